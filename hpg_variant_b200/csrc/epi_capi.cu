@@ -1,0 +1,725 @@
+// epi_capi.cu -- implementation of include/hpgv_epi.h on top of the kernels in
+// epi_kernels.cuh.  Host side: context, dataset upload, fold layout, work-list
+// construction, kernel dispatch.  No CPU compute path exists in this file: every
+// count, risk flag, accuracy and ranking decision is made by a CUDA kernel.
+#include "../../include/hpgv_epi.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "epi_kernels.cuh"
+
+using namespace hpgv;
+
+static_assert(sizeof(hpgv_epi_model_t) == 40, "hpgv_epi_model_t must be 40 bytes");
+static_assert(sizeof(ModelOut) == sizeof(hpgv_epi_model_t), "device/host model records differ");
+static_assert(kMaxFolds == HPGV_MAX_FOLDS && kMaxRank == HPGV_MAX_RANK, "limits out of sync with hpgv_epi.h");
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;   // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct hpgv_epi_ctx {
+    int device = 0;
+    int num_sms = 0;
+    int max_smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    // dataset
+    const uint8_t *d_raw = nullptr;
+    DevBuf<uint8_t> raw_owned;
+    int64_t nv = 0;
+    int A = 0, U = 0;
+
+    // fold layout + packed planes
+    bool folds_set = false;
+    FoldLayout fl{};
+    int cbits = 8;
+    bool single = true;
+    int64_t snp_pad = 0;
+    int64_t npos = 0;                     // bit positions per SNP row = nblocks * bw * 32
+    std::vector<int32_t> perm;
+    std::vector<uint16_t> blk;
+    DevBuf<FoldLayout> d_fl;
+    DevBuf<int32_t> d_perm;
+    DevBuf<uint16_t> d_blk;
+    DevBuf<uint32_t> d_planes;
+    size_t plane_words = 0;
+
+    // search scratch
+    DevBuf<Cand> d_lists;
+    DevBuf<int> d_list_cnt;
+    DevBuf<long long> d_gthr;
+    DevBuf<unsigned long long> d_counter;
+    DevBuf<int64_t> d_prefix;
+    DevBuf<int32_t> d_jt0;
+    DevBuf<int> d_sel;
+    DevBuf<hpgv_epi_model_t> d_out;
+    DevBuf<Cand> d_merge_in;
+    // cached work list
+    int wl_order = 0, wl_ti = 0;
+    uint64_t wl_first = 0, wl_last = 0;
+    int64_t wl_nv = -1;
+    int wl_it0 = 0, wl_nit = 0;
+    int64_t wl_units = 0;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                         \
+            return HPGV_E_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+#define FAIL(code, msg)       \
+    do {                      \
+        ctx->err = (msg);     \
+        return (code);        \
+    } while (0)
+
+// ---------------------------------------------------------------------------------
+// reset kernel: work counter and global thresholds
+// ---------------------------------------------------------------------------------
+__global__ void reset_search_kernel(unsigned long long *counter, long long *gthr) {
+    if (threadIdx.x == 0) *counter = 0ULL;
+    if (threadIdx.x < kMaxFolds) gthr[threadIdx.x] = LLONG_MIN;
+}
+
+// ---------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------
+extern "C" int hpgv_epi_create(int device, hpgv_epi_ctx **out) {
+    if (!out) return HPGV_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                         " (this library has no CPU fallback)";
+        return HPGV_E_CUDA;
+    }
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= ndev) {
+        g_create_error = "device index out of range";
+        return HPGV_E_ARG;
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return HPGV_E_CUDA;
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        g_create_error = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+        return HPGV_E_CUDA;
+    }
+    if (prop.major < 10) {
+        g_create_error = "device is not Blackwell (sm_100a kernels only); found sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+        return HPGV_E_UNSUPPORTED;
+    }
+    hpgv_epi_ctx *ctx = new hpgv_epi_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int) prop.sharedMemPerBlockOptin;
+    *out = ctx;
+    return HPGV_OK;
+}
+
+extern "C" void hpgv_epi_destroy(hpgv_epi_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    ctx->raw_owned.release(); ctx->d_fl.release(); ctx->d_perm.release(); ctx->d_blk.release(); ctx->d_planes.release();
+    ctx->d_lists.release(); ctx->d_list_cnt.release(); ctx->d_gthr.release(); ctx->d_counter.release();
+    ctx->d_prefix.release(); ctx->d_jt0.release(); ctx->d_sel.release(); ctx->d_out.release(); ctx->d_merge_in.release();
+    delete ctx;
+}
+
+extern "C" const char *hpgv_epi_last_error(const hpgv_epi_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int hpgv_epi_set_stream(hpgv_epi_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return HPGV_E_ARG;
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    return HPGV_OK;
+}
+
+extern "C" int64_t hpgv_epi_launch_count(const hpgv_epi_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------------
+// dataset
+// ---------------------------------------------------------------------------------
+static int set_dims(hpgv_epi_ctx *ctx, int64_t nv, int A, int U) {
+    if (nv < 2 || nv > (int64_t) INT32_MAX - 4096) FAIL(HPGV_E_ARG, "num_variants must be in [2, 2^31)");
+    if (A < 1 || U < 1) FAIL(HPGV_E_ARG, "need at least one affected and one unaffected sample");
+    ctx->nv = nv; ctx->A = A; ctx->U = U;
+    ctx->folds_set = false;
+    ctx->wl_nv = -1;
+    return HPGV_OK;
+}
+
+extern "C" int hpgv_epi_load_dataset_host(hpgv_epi_ctx *ctx, const uint8_t *genotypes, int64_t nv, int A, int U) {
+    if (!ctx || !genotypes) return HPGV_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc = set_dims(ctx, nv, A, U);
+    if (rc) return rc;
+    const size_t bytes = (size_t) nv * (size_t) (A + U);
+    CK(ctx->raw_owned.reserve(bytes));
+    CK(cudaMemcpyAsync(ctx->raw_owned.p, genotypes, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->d_raw = ctx->raw_owned.p;
+    return HPGV_OK;
+}
+
+extern "C" int hpgv_epi_load_dataset_device(hpgv_epi_ctx *ctx, const uint8_t *d_genotypes, int64_t nv, int A, int U) {
+    if (!ctx || !d_genotypes) return HPGV_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc = set_dims(ctx, nv, A, U);
+    if (rc) return rc;
+    ctx->d_raw = d_genotypes;
+    return HPGV_OK;
+}
+
+extern "C" int hpgv_epi_load_dataset_file(hpgv_epi_ctx *ctx, const char *path) {
+    if (!ctx || !path) return HPGV_E_ARG;
+    FILE *fp = fopen(path, "rb");
+    if (!fp) FAIL(HPGV_E_IO, std::string("cannot open dataset file ") + path);
+    fseek(fp, 0, SEEK_END);
+    const long long len = ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    unsigned char hdr[16] = {0};
+    const size_t got = fread(hdr, 1, 16, fp);
+    if (got < 12) { fclose(fp); FAIL(HPGV_E_IO, "dataset file shorter than its header"); }
+    // current format: 3 x uint32 (dataset.c:58-63); legacy fixture: size_t + 2 x uint32
+    uint32_t h32[4];
+    memcpy(h32, hdr, 16);
+    long long nv = 0, A = 0, U = 0, off = 0;
+    auto fits = [&](long long n, long long a, long long u, long long o, long long slack) {
+        return n >= 1 && a >= 1 && u >= 1 && len >= o + n * (a + u) && len <= o + n * (a + u) + slack;
+    };
+    if (fits(h32[0], h32[1], h32[2], 12, 0)) { nv = h32[0]; A = h32[1]; U = h32[2]; off = 12; }
+    else if (got == 16 && h32[1] == 0 && fits(h32[0], h32[2], h32[3], 16, 7)) { nv = h32[0]; A = h32[2]; U = h32[3]; off = 16; }
+    else if (fits(h32[0], h32[1], h32[2], 12, 7)) { nv = h32[0]; A = h32[1]; U = h32[2]; off = 12; }
+    else { fclose(fp); FAIL(HPGV_E_IO, "dataset header does not match the file length (neither 12-byte nor legacy 16-byte layout)"); }
+    const size_t bytes = (size_t) nv * (size_t) (A + U);
+    uint8_t *host = nullptr;
+    if (cudaMallocHost(&host, bytes) != cudaSuccess) { fclose(fp); FAIL(HPGV_E_NOMEM, "cannot allocate pinned staging buffer"); }
+    fseek(fp, (long) off, SEEK_SET);
+    const size_t rd = fread(host, 1, bytes, fp);
+    fclose(fp);
+    int rc = HPGV_OK;
+    if (rd != bytes) { ctx->err = "short read of the genotype matrix"; rc = HPGV_E_IO; }
+    if (!rc) rc = hpgv_epi_load_dataset_host(ctx, host, nv, (int) A, (int) U);
+    if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "H2D copy failed"; rc = HPGV_E_CUDA; }
+    cudaFreeHost(host);
+    return rc;
+}
+
+extern "C" int hpgv_epi_dataset_dims(const hpgv_epi_ctx *ctx, int64_t *nv, int *A, int *U) {
+    if (!ctx || !ctx->d_raw) return HPGV_E_STATE;
+    if (nv) *nv = ctx->nv;
+    if (A) *A = ctx->A;
+    if (U) *U = ctx->U;
+    return HPGV_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// folds
+// ---------------------------------------------------------------------------------
+extern "C" int hpgv_epi_set_folds(hpgv_epi_ctx *ctx, int F, const int32_t *fold_of_sample) {
+    if (!ctx || !fold_of_sample) return HPGV_E_ARG;
+    if (!ctx->d_raw) FAIL(HPGV_E_STATE, "set_folds before a dataset was loaded");
+    if (F < 2 || F > kMaxFolds) FAIL(HPGV_E_ARG, "num_folds must be in [2, 32]");
+    CK(cudaSetDevice(ctx->device));
+    const int A = ctx->A, U = ctx->U, S = A + U;
+
+    FoldLayout fl{};
+    fl.F = F; fl.nseg = 2 * F; fl.A = A; fl.U = U;
+    fl.balanced = (A == U);
+    fl.ratio = (float) A / (float) U;                 // mdr.c:52
+    std::vector<int> seg_size(2 * F, 0);
+    for (int s = 0; s < S; s++) {
+        const int f = fold_of_sample[s];
+        if (f < 0 || f >= F) FAIL(HPGV_E_ARG, "fold_of_sample holds a fold id outside [0, num_folds)");
+        seg_size[2 * f + (s < A ? 0 : 1)]++;
+    }
+    int max_seg = 0;
+    for (int f = 0; f < F; f++) {
+        fl.a_in[f] = seg_size[2 * f]; fl.u_in[f] = seg_size[2 * f + 1];
+        max_seg = std::max(max_seg, std::max(fl.a_in[f], fl.u_in[f]));
+    }
+    if (max_seg > 65535) FAIL(HPGV_E_UNSUPPORTED, "more than 65535 samples of one class in one fold");
+    if ((long long) A * U >= (1LL << 62)) FAIL(HPGV_E_UNSUPPORTED, "cohort too large");
+    fl.bw = max_seg <= 128 ? 4 : 8;
+    ctx->cbits = max_seg <= 255 ? 8 : 16;
+    const int bits_per_block = 32 * fl.bw;
+    std::vector<int> seg_blocks(2 * F), seg_first(2 * F);
+    int nb = 0;
+    for (int s = 0; s < 2 * F; s++) {
+        seg_blocks[s] = std::max(1, (seg_size[s] + bits_per_block - 1) / bits_per_block);
+        seg_first[s] = nb;
+        nb += seg_blocks[s];
+    }
+    if (nb > kMaxBlocks) FAIL(HPGV_E_UNSUPPORTED, "sample axis needs more than 8192 blocks");
+    fl.nblocks = nb;
+    ctx->single = (nb == 2 * F);
+    ctx->blk.assign(nb, 0);
+    for (int s = 0; s < 2 * F; s++)
+        for (int b = 0; b < seg_blocks[s]; b++)
+            ctx->blk[seg_first[s] + b] = (uint16_t) (s | (b == seg_blocks[s] - 1 ? 0x8000 : 0));
+    ctx->npos = (int64_t) nb * bits_per_block;
+    ctx->perm.assign((size_t) ctx->npos, -1);
+    {
+        std::vector<int> fill(2 * F, 0);
+        for (int s = 0; s < S; s++) {       // ascending dataset column inside each segment
+            const int seg = 2 * fold_of_sample[s] + (s < A ? 0 : 1);
+            ctx->perm[(size_t) seg_first[seg] * bits_per_block + fill[seg]++] = s;
+        }
+    }
+    ctx->fl = fl;
+    // rows are padded so that every tile a kernel stages (<= 32 rows past any valid origin) stays inside the buffer
+    ctx->snp_pad = ((ctx->nv + kTileJ - 1) / kTileJ) * kTileJ + kTileJ;
+    ctx->plane_words = (size_t) nb * (size_t) ctx->snp_pad * 3 * fl.bw;
+
+    CK(ctx->d_fl.reserve(1));
+    CK(ctx->d_perm.reserve(ctx->perm.size()));
+    CK(ctx->d_blk.reserve(ctx->blk.size()));
+    CK(ctx->d_planes.reserve(ctx->plane_words));
+    CK(cudaMemcpyAsync(ctx->d_fl.p, &ctx->fl, sizeof(FoldLayout), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_perm.p, ctx->perm.data(), ctx->perm.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_blk.p, ctx->blk.data(), ctx->blk.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_planes.p, 0, ctx->plane_words * sizeof(uint32_t), ctx->stream));
+
+    const int64_t warps = ctx->nv * (int64_t) nb * fl.bw;
+    const int threads = 256;
+    const int64_t blocks = (warps * 32 + threads - 1) / threads;
+    if (blocks > INT32_MAX) FAIL(HPGV_E_UNSUPPORTED, "dataset too large for the packer grid");
+    if (fl.bw == 4)
+        pack_planes_kernel<4><<<(unsigned) blocks, threads, 0, ctx->stream>>>(ctx->d_raw, ctx->nv, S, ctx->d_perm.p, nb, ctx->snp_pad, ctx->d_planes.p);
+    else
+        pack_planes_kernel<8><<<(unsigned) blocks, threads, 0, ctx->stream>>>(ctx->d_raw, ctx->nv, S, ctx->d_perm.p, nb, ctx->snp_pad, ctx->d_planes.p);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    // perm/blk host vectors are read by the async copies above
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->folds_set = true;
+    return HPGV_OK;
+}
+
+// drand48-compatible generator (48-bit LCG of POSIX): the reference shuffles with
+// srand48(seed) + drand48() (lib/c/src/math/data/array_utils.c:173-188)
+namespace {
+struct Rand48 {
+    uint64_t x;
+    explicit Rand48(long seed) : x((((uint64_t) (uint32_t) seed) << 16) | 0x330EULL) {}
+    double next() {
+        x = (x * 0x5DEECE66DULL + 0xBULL) & ((1ULL << 48) - 1);
+        return (double) x / 281474976710656.0;
+    }
+};
+void shuffle48(int *v, size_t n, long seed) {
+    if (n <= 1) return;
+    Rand48 rng(seed);
+    for (size_t i = n - 1; i > 0; i--) {
+        size_t j = (unsigned int) (rng.next() * (double) (i + 1));
+        std::swap(v[i], v[j]);
+    }
+}
+}  // namespace
+
+extern "C" int hpgv_epi_k_folds(int A, int U, int k, long seed, int32_t *fold_of_sample, uint32_t *sizes) {
+    if (A < 0 || U < 0 || k < 1 || !fold_of_sample) return HPGV_E_ARG;
+    std::vector<int> samples((size_t) A + U);
+    for (int i = 0; i < A + U; i++) samples[i] = i;
+    shuffle48(samples.data(), (size_t) A, seed);          // cases and controls separately (cross_validation.c:20-21)
+    shuffle48(samples.data() + A, (size_t) U, seed);
+    std::vector<uint32_t> fs(3 * (size_t) k, 0);
+    // round-robin deal, one case and one control per fold per pass (cross_validation.c:45-67)
+    for (int i = 0; i < A; i++) { fold_of_sample[samples[i]] = i % k; fs[3 * (i % k) + 1]++; }
+    for (int i = 0; i < U; i++) { fold_of_sample[samples[A + i]] = i % k; fs[3 * (i % k) + 2]++; }
+    for (int f = 0; f < k; f++) fs[3 * f] = fs[3 * f + 1] + fs[3 * f + 2];
+    if (sizes) memcpy(sizes, fs.data(), fs.size() * sizeof(uint32_t));
+    return HPGV_OK;
+}
+
+extern "C" uint64_t hpgv_epi_num_combinations(int64_t nv, int order) {
+    if (nv < order) return 0;
+    if (order == 2) return choose2((uint64_t) nv);
+    if (order == 3) return choose3((uint64_t) nv);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// search
+// ---------------------------------------------------------------------------------
+namespace {
+
+// (i, j) of linear pair index idx
+void unrank_pair(uint64_t n, uint64_t idx, int64_t *i_out, int64_t *j_out) {
+    // offset(i) = i(2n-i-1)/2 ; find the largest i with offset(i) <= idx
+    double nn = (double) n;
+    double disc = (2 * nn - 1) * (2 * nn - 1) - 8.0 * (double) idx;
+    int64_t i = (int64_t) (((2 * nn - 1) - std::sqrt(std::max(0.0, disc))) / 2.0);
+    i = std::max<int64_t>(0, std::min<int64_t>(i, (int64_t) n - 2));
+    while (i > 0 && pair_index(n, (uint64_t) i, (uint64_t) i + 1) > idx) i--;
+    while (i + 1 <= (int64_t) n - 2 && pair_index(n, (uint64_t) i + 1, (uint64_t) i + 2) <= idx) i++;
+    *i_out = i;
+    *j_out = (int64_t) (idx - pair_index(n, (uint64_t) i, (uint64_t) i + 1)) + i + 1;
+}
+
+// first element of the triple with linear index idx
+int64_t unrank_triple_first(uint64_t n, uint64_t idx) {
+    int64_t lo = 0, hi = (int64_t) n - 3;     // largest i with (choose3(n) - choose3(n - i)) <= idx
+    const uint64_t c3n = choose3(n);
+    while (lo < hi) {
+        int64_t mid = (lo + hi + 1) / 2;
+        if (c3n - choose3(n - (uint64_t) mid) <= idx) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+template <typename K>
+cudaError_t opt_in_smem(K kernel, size_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+}
+
+size_t ctl_bytes() { return ((sizeof(SearchCtl) + 127) / 128) * 128; }
+
+}  // namespace
+
+static int build_worklist(hpgv_epi_ctx *ctx, int order, int ti, uint64_t first, uint64_t last) {
+    if (ctx->wl_nv == ctx->nv && ctx->wl_order == order && ctx->wl_ti == ti && ctx->wl_first == first && ctx->wl_last == last)
+        return HPGV_OK;
+    const int64_t nv = ctx->nv;
+    std::vector<int64_t> prefix;
+    std::vector<int32_t> jt0;
+    int it0 = 0;
+    int64_t units = 0;
+    if (first < last) {
+        if (order == 2) {
+            int64_t i_first, j_first, i_last, j_last;
+            unrank_pair((uint64_t) nv, first, &i_first, &j_first);
+            unrank_pair((uint64_t) nv, last - 1, &i_last, &j_last);
+            it0 = (int) (i_first / ti);
+            const int it1 = (int) (i_last / ti);
+            for (int t = it0; t <= it1; t++) {
+                int64_t jlo = INT64_MAX, jhi = -1;
+                for (int64_t r = std::max<int64_t>((int64_t) t * ti, i_first); r < (int64_t) (t + 1) * ti && r <= i_last && r <= nv - 2; r++) {
+                    const int64_t lo = (r == i_first) ? j_first : r + 1;
+                    const int64_t hi = (r == i_last) ? j_last : nv - 1;
+                    if (lo <= hi) { jlo = std::min(jlo, lo); jhi = std::max(jhi, hi); }
+                }
+                prefix.push_back(units);
+                if (jhi >= 0) { jt0.push_back((int32_t) (jlo / kTileJ)); units += jhi / kTileJ - jlo / kTileJ + 1; }
+                else jt0.push_back(0);
+            }
+        } else {
+            // super-unit = (row i, tile of kConsumerWarps j rows); the producer walks the k tiles
+            const int tj = kConsumerWarps;
+            const int64_t i_first = unrank_triple_first((uint64_t) nv, first);
+            const int64_t i_last = unrank_triple_first((uint64_t) nv, last - 1);
+            it0 = (int) i_first;
+            for (int64_t i = i_first; i <= i_last; i++) {
+                prefix.push_back(units);
+                const int64_t jlo = i + 1, jhi = nv - 2;
+                if (jlo <= jhi) { jt0.push_back((int32_t) (jlo / tj)); units += jhi / tj - jlo / tj + 1; }
+                else jt0.push_back(0);
+            }
+        }
+    }
+    if (prefix.empty()) { prefix.push_back(0); jt0.push_back(0); }
+    CK(ctx->d_prefix.reserve(prefix.size()));
+    CK(ctx->d_jt0.reserve(jt0.size()));
+    CK(cudaMemcpyAsync(ctx->d_prefix.p, prefix.data(), prefix.size() * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_jt0.p, jt0.data(), jt0.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
+    ctx->wl_nv = nv; ctx->wl_order = order; ctx->wl_ti = ti; ctx->wl_first = first; ctx->wl_last = last;
+    ctx->wl_it0 = it0; ctx->wl_nit = (int) prefix.size(); ctx->wl_units = units;
+    return HPGV_OK;
+}
+
+template <typename K>
+static int launch_search(hpgv_epi_ctx *ctx, K kernel, size_t smem, SearchArgs &args, int F, int rank) {
+    if (smem > (size_t) ctx->max_smem_optin)
+        FAIL(HPGV_E_UNSUPPORTED, "fold count x cell count needs " + std::to_string(smem) + " bytes of shared memory per CTA (limit " +
+                                     std::to_string(ctx->max_smem_optin) + ")");
+    CK(opt_in_smem(kernel, smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kSearchThreads, smem));
+    if (per_sm < 1) FAIL(HPGV_E_UNSUPPORTED, "search kernel does not fit on an SM");
+    int64_t grid = (int64_t) per_sm * ctx->num_sms;
+    grid = std::max<int64_t>(1, std::min<int64_t>(grid, std::max<int64_t>(args.num_units, 1)));
+    CK(ctx->d_lists.reserve((size_t) grid * F * rank));
+    CK(ctx->d_list_cnt.reserve((size_t) grid * F));
+    CK(ctx->d_gthr.reserve(kMaxFolds));
+    CK(ctx->d_counter.reserve(1));
+    args.lists = ctx->d_lists.p;
+    args.list_cnt = ctx->d_list_cnt.p;
+    args.gthr = ctx->d_gthr.p;
+    args.unit_counter = ctx->d_counter.p;
+    reset_search_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_counter.p, ctx->d_gthr.p);
+    CK(cudaGetLastError());
+    kernel<<<(unsigned) grid, kSearchThreads, smem, ctx->stream>>>(args);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+
+    CK(ctx->d_sel.reserve((size_t) F * grid * rank));   // scratch of the merge that follows
+    return (int) grid;
+}
+
+static int do_search(hpgv_epi_ctx *ctx, int order, int eval_subset, int rank, uint64_t first, uint64_t last,
+                     hpgv_epi_model_t *d_out) {
+    if (!ctx->folds_set) FAIL(HPGV_E_STATE, "search before set_folds");
+    if (order != 2 && order != 3) FAIL(HPGV_E_ARG, "order must be 2 or 3");
+    if (rank < 1 || rank > kMaxRank) FAIL(HPGV_E_ARG, "rank_size must be in [1, 4096]");
+    if (eval_subset != HPGV_SUBSET_TESTING && eval_subset != HPGV_SUBSET_TRAINING) FAIL(HPGV_E_ARG, "eval_subset must be 0 (testing) or 1 (training)");
+    if (ctx->nv < order) FAIL(HPGV_E_ARG, "fewer variants than the order");
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t total = hpgv_epi_num_combinations(ctx->nv, order);
+    if (last > total) last = total;
+    if (first > last) first = last;
+
+    const FoldLayout &fl = ctx->fl;
+    const int F = fl.F;
+    const int nwc = words_per_cell(fl.nseg, ctx->cbits);
+    SearchArgs args{};
+    args.planes = ctx->d_planes.p;
+    args.blk_desc = ctx->d_blk.p;
+    args.fl = ctx->d_fl.p;
+    args.snp_pad = ctx->snp_pad;
+    args.nv = (int) ctx->nv;
+    args.training = (eval_subset == HPGV_SUBSET_TRAINING);
+    args.rank = rank;
+    args.first = first;
+    args.last = last;
+
+    const int ppt = (order == 2) ? (ctx->cbits == 8 ? 2 : 1) : 1;
+    const int ti = (order == 2) ? kConsumerWarps * ppt : 1;
+    int rc = build_worklist(ctx, order, ti, first, last);
+    if (rc) return rc;
+    args.unit_prefix = ctx->d_prefix.p;
+    args.unit_jt0 = ctx->d_jt0.p;
+    args.it0 = ctx->wl_it0;
+    args.n_it = ctx->wl_nit;
+    args.num_units = ctx->wl_units;
+
+    int grid = 0;
+    if (order == 2) {
+        const size_t stage_bytes = (size_t) kStages * (ti + kTileJ) * 3 * fl.bw * 4;
+        const size_t smem = ctl_bytes() + stage_bytes + (size_t) ppt * 9 * nwc * kConsumers * 4;
+        if (fl.bw == 4) grid = launch_search(ctx, search2_kernel<4, 8, 2, true>, smem, args, F, rank);
+        else if (ctx->cbits == 8) grid = launch_search(ctx, search2_kernel<8, 8, 2, true>, smem, args, F, rank);
+        else grid = launch_search(ctx, search2_kernel<8, 16, 1, false>, smem, args, F, rank);
+    } else {
+        const size_t rows = 1 + kConsumerWarps + kTileJ;
+        const size_t stagew = ((rows * 3 * fl.bw + 3) / 4) * 4;
+        const size_t smem = ctl_bytes() + (size_t) kStages * stagew * 4 + (size_t) 27 * nwc * kConsumers * 4;
+        if (fl.bw == 4) grid = launch_search(ctx, search3_kernel<4, 8, true>, smem, args, F, rank);
+        else if (ctx->cbits == 8) grid = launch_search(ctx, search3_kernel<8, 8, true>, smem, args, F, rank);
+        else grid = launch_search(ctx, search3_kernel<8, 16, false>, smem, args, F, rank);
+    }
+    if (grid < 0) return grid;
+
+    MergeArgs m{};
+    m.lists = ctx->d_lists.p; m.list_cnt = ctx->d_list_cnt.p; m.gthr = ctx->d_gthr.p;
+    m.nlists = grid; m.F = F; m.rank_in = rank; m.rank_out = rank; m.training = args.training;
+    m.fl = ctx->d_fl.p; m.out = d_out; m.order = order; m.sel = ctx->d_sel.p;
+    merge_kernel<<<F, 1024, 0, ctx->stream>>>(m);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return HPGV_OK;
+}
+
+extern "C" int hpgv_epi_search_device(hpgv_epi_ctx *ctx, int order, int eval_subset, int rank, uint64_t first, uint64_t last,
+                                      hpgv_epi_model_t *d_out) {
+    if (!ctx || !d_out) return HPGV_E_ARG;
+    return do_search(ctx, order, eval_subset, rank, first, last, d_out);
+}
+
+extern "C" int hpgv_epi_search(hpgv_epi_ctx *ctx, int order, int eval_subset, int rank, uint64_t first, uint64_t last,
+                               hpgv_epi_model_t *out) {
+    if (!ctx || !out) return HPGV_E_ARG;
+    if (!ctx->folds_set) FAIL(HPGV_E_STATE, "search before set_folds");
+    if (rank < 1 || rank > kMaxRank) FAIL(HPGV_E_ARG, "rank_size must be in [1, 4096]");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t) ctx->fl.F * rank;
+    CK(ctx->d_out.reserve(n));
+    int rc = do_search(ctx, order, eval_subset, rank, first, last, ctx->d_out.p);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, ctx->d_out.p, n * sizeof(hpgv_epi_model_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HPGV_OK;
+}
+
+extern "C" int hpgv_epi_merge_device(hpgv_epi_ctx *ctx, int order, int eval_subset, int num_lists, int F, int rank,
+                                     const hpgv_epi_model_t *d_lists, hpgv_epi_model_t *d_out) {
+    if (!ctx || !d_lists || !d_out) return HPGV_E_ARG;
+    if (!ctx->folds_set) FAIL(HPGV_E_STATE, "merge before set_folds (fold sizes are needed)");
+    if (F != ctx->fl.F) FAIL(HPGV_E_ARG, "num_folds differs from the layout set by set_folds");
+    if (num_lists < 1 || rank < 1 || rank > kMaxRank) FAIL(HPGV_E_ARG, "bad list shape");
+    CK(cudaSetDevice(ctx->device));
+    const int64_t n = (int64_t) num_lists * F * rank;
+    CK(ctx->d_merge_in.reserve((size_t) n));
+    CK(ctx->d_sel.reserve((size_t) n));
+    models_to_cands_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const ModelOut *>(d_lists), n, ctx->d_merge_in.p);
+    CK(cudaGetLastError());
+    MergeArgs m{};
+    m.lists = ctx->d_merge_in.p; m.list_cnt = nullptr; m.gthr = nullptr;
+    m.nlists = num_lists; m.F = F; m.rank_in = rank; m.rank_out = rank;
+    m.training = (eval_subset == HPGV_SUBSET_TRAINING);
+    m.fl = ctx->d_fl.p; m.out = d_out; m.order = order; m.sel = ctx->d_sel.p;
+    merge_kernel<<<F, 1024, 0, ctx->stream>>>(m);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+    return HPGV_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// parity hooks
+// ---------------------------------------------------------------------------------
+extern "C" int hpgv_epi_eval(hpgv_epi_ctx *ctx, int order, int eval_subset, int64_t ncomb, const int32_t *combs,
+                             int32_t *counts_aff, int32_t *counts_unaff, uint32_t *risky_mask, uint32_t *conf, double *accuracy) {
+    if (!ctx || !combs || ncomb < 0) return HPGV_E_ARG;
+    if (!ctx->folds_set) FAIL(HPGV_E_STATE, "eval before set_folds");
+    if (order != 2 && order != 3) FAIL(HPGV_E_ARG, "order must be 2 or 3");
+    if (ncomb == 0) return HPGV_OK;
+    for (int64_t c = 0; c < ncomb; c++)
+        for (int o = 0; o < order; o++) {
+            const int32_t v = combs[c * order + o];
+            if (v < 0 || v >= ctx->nv || (o > 0 && v <= combs[c * order + o - 1])) FAIL(HPGV_E_ARG, "combination indices must be ascending and inside the dataset");
+        }
+    CK(cudaSetDevice(ctx->device));
+    const int F = ctx->fl.F, C = order == 2 ? 9 : 27;
+    const size_t nf = (size_t) ncomb * F;
+    int32_t *d_combs = nullptr, *d_ca = nullptr, *d_cu = nullptr;
+    uint32_t *d_mask = nullptr, *d_conf = nullptr;
+    double *d_acc = nullptr;
+    int rc = HPGV_OK;
+    auto cleanup = [&]() { cudaFree(d_combs); cudaFree(d_ca); cudaFree(d_cu); cudaFree(d_mask); cudaFree(d_conf); cudaFree(d_acc); };
+#define CKE(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); cleanup(); return HPGV_E_CUDA; } } while (0)
+    CKE(cudaMalloc(&d_combs, (size_t) ncomb * order * sizeof(int32_t)));
+    CKE(cudaMalloc(&d_ca, nf * C * sizeof(int32_t)));
+    CKE(cudaMalloc(&d_cu, nf * C * sizeof(int32_t)));
+    CKE(cudaMalloc(&d_mask, nf * sizeof(uint32_t)));
+    CKE(cudaMalloc(&d_conf, nf * 4 * sizeof(uint32_t)));
+    CKE(cudaMalloc(&d_acc, nf * sizeof(double)));
+    CKE(cudaMemcpyAsync(d_combs, combs, (size_t) ncomb * order * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    const int warps = 4;
+    const size_t smem = (size_t) warps * ctx->fl.nseg * C * sizeof(int);
+    const unsigned grid = (unsigned) ((ncomb + warps - 1) / warps);
+    const int training = (eval_subset == HPGV_SUBSET_TRAINING);
+    if (ctx->fl.bw == 4)
+        eval_kernel<4><<<grid, warps * 32, smem, ctx->stream>>>(ctx->d_planes.p, ctx->d_blk.p, ctx->d_fl.p, ctx->snp_pad, order, training, ncomb, d_combs, d_ca, d_cu, d_mask, d_conf, d_acc);
+    else
+        eval_kernel<8><<<grid, warps * 32, smem, ctx->stream>>>(ctx->d_planes.p, ctx->d_blk.p, ctx->d_fl.p, ctx->snp_pad, order, training, ncomb, d_combs, d_ca, d_cu, d_mask, d_conf, d_acc);
+    CKE(cudaGetLastError());
+    ctx->launches++;
+    if (counts_aff) CKE(cudaMemcpyAsync(counts_aff, d_ca, nf * C * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (counts_unaff) CKE(cudaMemcpyAsync(counts_unaff, d_cu, nf * C * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (risky_mask) CKE(cudaMemcpyAsync(risky_mask, d_mask, nf * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (conf) CKE(cudaMemcpyAsync(conf, d_conf, nf * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (accuracy) CKE(cudaMemcpyAsync(accuracy, d_acc, nf * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CKE(cudaStreamSynchronize(ctx->stream));
+#undef CKE
+    cleanup();
+    return rc;
+}
+
+extern "C" int hpgv_epi_unpack_masks(hpgv_epi_ctx *ctx, int64_t variant, uint8_t *out) {
+    if (!ctx || !out) return HPGV_E_ARG;
+    if (!ctx->folds_set) FAIL(HPGV_E_STATE, "unpack before set_folds");
+    if (variant < 0 || variant >= ctx->nv) FAIL(HPGV_E_ARG, "variant out of range");
+    CK(cudaSetDevice(ctx->device));
+    const int a_pad = 16 * ((ctx->A + 15) / 16), u_pad = 16 * ((ctx->U + 15) / 16), s_pad = a_pad + u_pad;
+    uint8_t *d_out = nullptr;
+    CK(cudaMalloc(&d_out, (size_t) 3 * s_pad));
+    cudaMemsetAsync(d_out, 0, (size_t) 3 * s_pad, ctx->stream);
+    const unsigned grid = (unsigned) ((ctx->npos + 255) / 256);
+    if (ctx->fl.bw == 4)
+        unpack_masks_kernel<4><<<grid, 256, 0, ctx->stream>>>(ctx->d_planes.p, variant, ctx->snp_pad, ctx->d_perm.p, ctx->npos, ctx->A, a_pad, s_pad, d_out);
+    else
+        unpack_masks_kernel<8><<<grid, 256, 0, ctx->stream>>>(ctx->d_planes.p, variant, ctx->snp_pad, ctx->d_perm.p, ctx->npos, ctx->A, a_pad, s_pad, d_out);
+    ctx->launches++;
+    cudaError_t e = cudaMemcpyAsync(out, d_out, (size_t) 3 * s_pad, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_out);
+    if (e != cudaSuccess) FAIL(HPGV_E_CUDA, std::string("unpack: ") + cudaGetErrorString(e));
+    return HPGV_OK;
+}
+
+extern "C" int hpgv_epi_run_host(hpgv_epi_ctx *ctx, const uint8_t *genotypes, int64_t nv, int A, int U, int F,
+                                 const int32_t *fold_of_sample, int order, int eval_subset, int rank,
+                                 uint64_t first, uint64_t last, hpgv_epi_model_t *out) {
+    int rc = hpgv_epi_load_dataset_host(ctx, genotypes, nv, A, U);
+    if (rc) return rc;
+    rc = hpgv_epi_set_folds(ctx, F, fold_of_sample);
+    if (rc) return rc;
+    return hpgv_epi_search(ctx, order, eval_subset, rank, first, last, out);
+}
+
+extern "C" int hpgv_epi_layout(const hpgv_epi_ctx *ctx, hpgv_epi_layout_t *out) {
+    if (!ctx || !out) return HPGV_E_ARG;
+    if (!ctx->folds_set) return HPGV_E_STATE;
+    out->num_folds = ctx->fl.F; out->num_segments = ctx->fl.nseg; out->num_blocks = ctx->fl.nblocks; out->block_words = ctx->fl.bw;
+    out->count_bits = ctx->cbits;
+    out->plane_bytes = (int64_t) ctx->plane_words * 4;
+    out->words_per_class_row = (ctx->A + 31) / 32 + (ctx->U + 31) / 32;
+    return HPGV_OK;
+}
+
+extern "C" int hpgv_epi_pipe_peak(hpgv_epi_ctx *ctx, int kind, int iters, double *ops_per_second) {
+    if (!ctx || !ops_per_second || iters < 1 || kind < 0 || kind > 2) return HPGV_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    uint32_t *d_sink = nullptr;
+    CK(cudaMalloc(&d_sink, 4));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int threads = 256, grid = ctx->num_sms * 8;
+    auto run = [&]() {
+        if (kind == 0) pipe_peak_kernel<0><<<grid, threads, 0, ctx->stream>>>(iters, 12345u, d_sink);
+        else if (kind == 1) pipe_peak_kernel<1><<<grid, threads, 0, ctx->stream>>>(iters, 12345u, d_sink);
+        else pipe_peak_kernel<2><<<grid, threads, 0, ctx->stream>>>(iters, 12345u, d_sink);
+    };
+    run();   // warm-up
+    cudaEventRecord(e0, ctx->stream);
+    run();
+    cudaEventRecord(e1, ctx->stream);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_sink);
+    ctx->launches += 2;
+    if (e != cudaSuccess) FAIL(HPGV_E_CUDA, std::string("pipe_peak: ") + cudaGetErrorString(e));
+    // ops counted per inner step: kind 0 -> 1 POPC, kind 1 -> 2 LOP3, kind 2 -> 2 LOP3 + 1 POPC (reported as 3)
+    const double per_step = kind == 0 ? 1.0 : (kind == 1 ? 2.0 : 3.0);
+    *ops_per_second = per_step * 64.0 * (double) iters * threads * (double) grid / (ms * 1e-3);
+    return HPGV_OK;
+}

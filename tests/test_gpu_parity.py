@@ -1,0 +1,145 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the CPU oracle on the same
+seeded inputs.  Bit-exact for counts, risk masks, confusion matrices and selected
+models; balanced accuracy to 1e-12 (it is computed from the same integers in
+double on both sides, so the tests actually demand equality)."""
+import numpy as np
+import pytest
+
+import hpg_variant_b200 as h
+from hpg_variant_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+BA_TOL = 1e-12
+
+
+def random_folds(rng, A, U, F):
+    fos = np.concatenate([rng.permutation(A) % F, rng.permutation(U) % F]).astype(np.int32)
+    return fos
+
+
+def all_combs(nv, order):
+    import itertools
+    return np.array(list(itertools.combinations(range(nv), order)), np.int32)
+
+
+def check_eval(engine, oracle, g, A, U, F, fos, order, combs, subset):
+    engine.load_dataset(g, A, U)
+    engine.set_folds(F, fos)
+    got = engine.eval(order, combs, subset)
+    want = oracle.eval(g, A, U, order, fos, subset, combs)
+    for k in ("counts_aff", "counts_unaff", "risky_mask", "conf"):
+        assert np.array_equal(got[k], want[k]), k
+    assert np.array_equal(np.isnan(got["ba"]), np.isnan(want["ba"]))
+    ok = ~np.isnan(want["ba"])
+    assert np.max(np.abs(got["ba"][ok] - want["ba"][ok]), initial=0.0) <= BA_TOL
+    assert np.array_equal(got["ba"][ok], want["ba"][ok])   # same integers, same double ops
+    return got
+
+
+SHAPES = [
+    # nv, A, U, F   (layout exercised)
+    (12, 49, 98, 10),      # BW=4, unbalanced (float32 rule slow path), fixture-like sizes
+    (10, 64, 64, 4),       # BW=4, balanced, segment = 16
+    (9, 700, 700, 5),      # BW=8 single block (140 per segment), u8 counters
+    (8, 1300, 900, 3),     # BW=8, 2 blocks per segment (434, 300), u16 counters, unbalanced
+    (7, 5000, 5000, 2),    # many blocks per segment, u16
+    (6, 33, 17, 2),        # ragged tiny
+]
+
+
+@pytest.mark.parametrize("nv,A,U,F", SHAPES)
+@pytest.mark.parametrize("order", [2, 3])
+@pytest.mark.parametrize("subset", [h.SUBSET_TRAINING, h.SUBSET_TESTING])
+def test_eval_matches_oracle(engine, oracle, nv, A, U, F, order, subset):
+    rng = np.random.default_rng(nv * 1000 + A + F + order)
+    g = synth.make_dataset(nv, A, U, seed=A + U + nv, order=order, missing=0.02, planted=1)
+    fos = random_folds(rng, A, U, F)
+    check_eval(engine, oracle, g, A, U, F, fos, order, all_combs(nv, order), subset)
+
+
+def compare_models(got, want, order):
+    assert got.shape == want.shape
+    assert np.array_equal(got["snp"][..., :order], want["snp"][..., :order])
+    assert np.array_equal(got["risky_mask"], want["risky_mask"])
+    assert np.array_equal(got["conf"], want["conf"])
+    gn, wn = np.isnan(got["accuracy"]), np.isnan(want["ba"])
+    assert np.array_equal(gn, wn)
+    assert np.array_equal(got["accuracy"][~gn], want["ba"][~wn])
+
+
+SEARCH_SHAPES = [
+    # nv, A, U, F, rank
+    (40, 49, 98, 10, 50),
+    (70, 100, 100, 10, 50),      # BW=4 balanced
+    (100, 1000, 1000, 10, 50),   # c2-shaped samples (BW=4, 100 per segment)
+    (90, 2000, 2000, 10, 20),    # c3-shaped samples (BW=8 single, u8)
+    (50, 1500, 1100, 4, 30),     # u16 multi-block, unbalanced
+    (37, 300, 200, 3, 700),      # rank > number of pairs: every pair comes back, sorted
+]
+
+
+@pytest.mark.parametrize("nv,A,U,F,rank", SEARCH_SHAPES)
+@pytest.mark.parametrize("subset", [h.SUBSET_TRAINING, h.SUBSET_TESTING])
+def test_search_order2_matches_oracle(engine, oracle, nv, A, U, F, rank, subset):
+    rng = np.random.default_rng(nv + A + F)
+    g = synth.make_dataset(nv, A, U, seed=nv * 7 + F, missing=0.01, planted=2)
+    fos = random_folds(rng, A, U, F)
+    engine.load_dataset(g, A, U)
+    engine.set_folds(F, fos)
+    got = engine.search(2, subset, rank)
+    want, _ = oracle.search(g, A, U, 2, fos, subset, rank, threads=8, num_folds=F)
+    compare_models(got, want, 2)
+
+
+@pytest.mark.parametrize("nv,A,U,F,rank", [(24, 49, 98, 5, 50), (30, 400, 400, 5, 40), (20, 2000, 2000, 5, 25), (18, 700, 500, 3, 1000)])
+@pytest.mark.parametrize("subset", [h.SUBSET_TRAINING, h.SUBSET_TESTING])
+def test_search_order3_matches_oracle(engine, oracle, nv, A, U, F, rank, subset):
+    rng = np.random.default_rng(nv + A + F + 3)
+    g = synth.make_dataset(nv, A, U, seed=nv * 11 + F, order=3, missing=0.01, planted=1)
+    fos = random_folds(rng, A, U, F)
+    engine.load_dataset(g, A, U)
+    engine.set_folds(F, fos)
+    got = engine.search(3, subset, rank)
+    want, _ = oracle.search(g, A, U, 3, fos, subset, rank, threads=8, num_folds=F)
+    compare_models(got, want, 3)
+
+
+def test_search_ranges_partition(engine, oracle):
+    """Contiguous index ranges (the multi-GPU sharding) merged on the GPU == one full search."""
+    import torch
+    nv, A, U, F, rank = 120, 500, 500, 5, 40
+    g = synth.make_dataset(nv, A, U, seed=5)
+    fos = random_folds(np.random.default_rng(1), A, U, F)
+    engine.load_dataset(g, A, U)
+    engine.set_folds(F, fos)
+    full = engine.search(2, h.SUBSET_TRAINING, rank)
+    total = h.num_combinations(nv, 2)
+    cuts = [0, total // 7, total // 3, total // 2 + 11, total]
+    parts = [engine.search(2, h.SUBSET_TRAINING, rank, cuts[i], cuts[i + 1]) for i in range(4)]
+    lists = torch.from_numpy(np.stack(parts).view(np.uint8)).cuda()
+    out = torch.zeros(F * rank * 40, dtype=torch.uint8, device="cuda")
+    engine.merge_device(2, h.SUBSET_TRAINING, 4, rank, lists.data_ptr(), out.data_ptr())
+    torch.cuda.synchronize()
+    merged = out.cpu().numpy().view(h.MODEL_DTYPE).reshape(F, rank)
+    assert merged.tobytes() == full.tobytes()
+    for p, (lo, hi) in zip(parts, zip(cuts[:-1], cuts[1:])):
+        want, _ = oracle.search(g, A, U, 2, fos, h.SUBSET_TRAINING, rank, first=lo, last=hi, threads=4, num_folds=F)
+        compare_models(p, want, 2)
+
+
+def test_packer_roundtrip(engine, oracle):
+    """unpack(pack(bytes)) == set_genotypes_masks of the reference (model.c:28-74), folds shuffled."""
+    nv, A, U, F = 5, 77, 130, 7
+    g = synth.make_dataset(nv, A, U, seed=3, missing=0.05, planted=0)
+    fos = random_folds(np.random.default_rng(2), A, U, F)
+    engine.load_dataset(g, A, U)
+    engine.set_folds(F, fos)
+    a_pad = 16 * ((A + 15) // 16)
+    for v in range(nv):
+        m = engine.unpack_masks(v)
+        for gt in range(3):
+            want = np.zeros(m.shape[1], np.uint8)
+            want[:A] = np.where(g[v, :A] == gt, 255, 0)
+            want[a_pad:a_pad + U] = np.where(g[v, A:] == gt, 255, 0)
+            assert np.array_equal(m[gt], want)
