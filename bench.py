@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the exhaustive epistasis search (MDR + k-fold CV) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|c5]
+
+One "step" = one pass of the hot path over one synthetic dataset: pack the bit planes for the
+fold assignment, evaluate every SNP combination for every fold, rank, merge.  Metric (BASELINE.json):
+SNP-combinations x folds evaluated per second.
+
+  value      device-resident: raw genotype bytes already in HBM, CUDA-event time of pack+search+merge
+             (+ NCCL all-gather + merge of the per-rank top-N when N > 1), max over ranks
+  e2e        the same through hpgv_epi_run_host with HOST (pinned) buffers: H2D of the genotype bytes,
+             pack, search, merge, D2H of the ranked models -- wall clock between device synchronisations
+  roofline   the search kernel alone (CUDA events recorded around its launch by the library) against the
+             POPC-pipe peak measured by a micro-benchmark in the same run; HBM figures alongside
+  cpu_baseline  the reference's own run_epistasis (oracle/_ref, OpenMP, all host cores) on a bounded
+             SNP-prefix sample of the same workload
+
+N = 1 runs BASELINE.json configs[1] ("c2": 10k SNPs x 2k samples, order 2, 10 folds).  N > 1 is weak
+scaling: the c2 sample shape with 10k*sqrt(N) SNPs (N x the combinations), the linear combination
+index space split into N contiguous ranges, one per rank; only the per-rank top-N lists cross NVLink.
+"""
+import argparse
+import json
+import math
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "SNP-combinations x folds evaluated/sec"
+UNIT = "comb*folds/s"
+RANK_SIZE = 50
+FOLD_SEED = 20261017
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--snps", type=int, default=0, help="override the SNP count of the workload")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="keep the total work fixed when N > 1")
+    return ap.parse_args()
+
+
+def workload(args, world):
+    from hpg_variant_b200 import synth
+    nv, A, U, order, folds, seed = synth.CONFIGS[args.workload]
+    if args.snps:
+        nv = args.snps
+    scaling = "weak"
+    if world > 1:
+        if args.strong:
+            scaling = "strong"
+        else:
+            nv = int(round(nv * world ** (1.0 / order)))
+    name = {"c2": "c2: synthetic 10k SNPs x 2k samples (1k cases/1k controls), order 2, 10-fold CV",
+            "c3": "c3: synthetic 100k SNPs x 4k samples, order 2, 10-fold CV",
+            "c4": "c4: synthetic 5k SNPs x 4k samples, order 3, 5-fold CV",
+            "c5": "c5: synthetic 20k SNPs x 50k samples, order 2, 10-fold CV"}[args.workload]
+    return dict(name=name, nv=nv, A=A, U=U, order=order, folds=folds, seed=seed, scaling=scaling)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi during the timed region
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        if not shutil.which("nvidia-smi"):
+            return
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0]))
+                smax = float(p[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline = the reference's own run_epistasis (or the oracle port when _ref is not built)
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_run(g, A, U, order, folds, nv_sub, threads):
+    """Times one reference run on the first nv_sub SNPs; returns (comb*folds/s, seconds, kind)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from hpg_variant_b200 import synth
+    sub = np.ascontiguousarray(g[:nv_sub])
+    ncomb = math.comb(nv_sub, order)
+    if oracle_lib.available("ref"):
+        ref = oracle_lib.Checker("ref")
+        tmp = tempfile.mkdtemp(prefix="hpgv_bench_")
+        try:
+            path = os.path.join(tmp, "sub.bin")
+            synth.write_dataset(path, sub, A, U)
+            # order 3: the reference only enumerates all triples with a single block => stride = nv_sub
+            stride = 100 if order == 2 else nv_sub
+            t0 = time.perf_counter()
+            ref.run_epistasis(path, os.path.join(tmp, "out"), order, stride, folds, 1, RANK_SIZE, 1, 1, threads)
+            dt = time.perf_counter() - t0
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        used = threads if order == 2 else 1     # one block = one OpenMP task
+        return ncomb * folds / dt, dt, "reference", used
+    import hpg_variant_b200 as h
+    orc = oracle_lib.Checker("oracle")
+    fos, _ = h.k_folds(A, U, folds, FOLD_SEED)
+    t0 = time.perf_counter()
+    orc.search(sub, A, U, order, fos, 1, RANK_SIZE, threads=threads, num_folds=folds)
+    dt = time.perf_counter() - t0
+    return ncomb * folds / dt, dt, "port", threads
+
+
+def sized_sample(order, nv, target_seconds, rate_comb_per_s):
+    want = max(1.0, target_seconds * rate_comb_per_s)
+    if order == 2:
+        n = int((1 + math.sqrt(1 + 8 * want)) / 2)
+    else:
+        n = int(round((6 * want) ** (1 / 3))) + 2
+    return max(order + 14, min(nv, n))
+
+
+def cpu_baseline(g, w, target_seconds=12.0):
+    threads = os.cpu_count() or 1
+    order = w["order"]
+    # calibration on a tiny prefix, then the bounded sample
+    n0 = sized_sample(order, w["nv"], 1.0, 20000.0 * (threads if order == 2 else 1))
+    rate0, _, kind, used = cpu_reference_run(g, w["A"], w["U"], order, w["folds"], n0, threads)
+    n1 = sized_sample(order, w["nv"], target_seconds, rate0 / w["folds"])
+    rate, dt, kind, used = cpu_reference_run(g, w["A"], w["U"], order, w["folds"], n1, threads)
+    return {"value": rate, "unit": UNIT, "cores": used, "kind": kind,
+            "sample": f"first {n1} SNPs of the workload ({math.comb(n1, order)} combinations x {w['folds']} folds), "
+                      f"{'run_epistasis of the reference (OpenMP, stride ' + ('100' if order == 2 else str(n1)) + ')' if kind == 'reference' else 'oracle port (OpenMP)'}, "
+                      f"{dt:.1f} s on {used} threads"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from hpg_variant_b200 import synth
+    w = workload(args, 1)
+    threads = os.cpu_count() or 1
+    # only a SNP prefix is ever timed: generate just that much
+    nv_gen = min(w["nv"], 6000 if w["order"] == 2 else 400)
+    g = synth.make_dataset(nv_gen, w["A"], w["U"], w["seed"], order=w["order"])
+    w_gen = dict(w, nv=nv_gen)
+    order = w["order"]
+    n0 = sized_sample(order, nv_gen, 1.0, 20000.0 * (threads if order == 2 else 1))
+    rate0, _, kind, used = cpu_reference_run(g, w["A"], w["U"], order, w["folds"], n0, threads)
+    total_budget = 150.0
+    per_step = max(1.0, min(8.0, total_budget / max(1, args.steps + args.warmup)))
+    n1 = sized_sample(order, nv_gen, per_step, rate0 / w["folds"])
+    for _ in range(args.warmup):
+        cpu_reference_run(g, w["A"], w["U"], order, w["folds"], n1, threads)
+    times, rates = [], []
+    for _ in range(args.steps):
+        r, dt, kind, used = cpu_reference_run(g, w["A"], w["U"], order, w["folds"], n1, threads)
+        times.append(dt)
+        rates.append(r)
+    ncomb = math.comb(n1, order)
+    value = ncomb * w["folds"] * len(times) / sum(times)
+    sample = (f"first {n1} SNPs of the workload ({ncomb} combinations x {w['folds']} folds) per step, "
+              f"{'the reference run_epistasis (OpenMP)' if kind == 'reference' else 'oracle port (OpenMP)'} on {used} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": w["name"], "order": order, "num_variants": w["nv"], "num_affected": w["A"], "num_unaffected": w["U"],
+                   "num_folds": w["folds"], "rank_size": RANK_SIZE, "eval_subset": "training", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import hpg_variant_b200 as h
+    from hpg_variant_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- hpg_variant_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    w = workload(args, world)
+    nv, A, U, order, F = w["nv"], w["A"], w["U"], w["order"], w["folds"]
+    S = A + U
+    total = h.num_combinations(nv, order)
+    first, last = total * rank // world, total * (rank + 1) // world
+
+    g_pinned = torch.empty((nv, S), dtype=torch.uint8).pin_memory()
+    g = g_pinned.numpy()
+    synth.make_dataset(nv, A, U, w["seed"], order=order, out=g)
+    fos, _ = h.k_folds(A, U, F, FOLD_SEED)
+
+    eng = h.EpistasisEngine(local_rank)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    d_raw = g_pinned.cuda(non_blocking=False)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    rec_bytes = F * RANK_SIZE * 40
+    d_local = torch.zeros(rec_bytes, dtype=torch.uint8, device="cuda")
+    d_all = torch.zeros(world * rec_bytes, dtype=torch.uint8, device="cuda")
+    d_final = torch.zeros(rec_bytes, dtype=torch.uint8, device="cuda")
+    h_out = np.zeros((F, RANK_SIZE), h.MODEL_DTYPE)
+
+    def step_device():
+        """pack + search (+ all-gather + merge) with the genotype bytes resident in HBM"""
+        eng.load_dataset_device(d_raw.data_ptr(), nv, A, U)
+        eng.set_folds(F, fos)
+        eng.search_device(order, h.SUBSET_TRAINING, RANK_SIZE, first, last, d_local.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_local)
+            eng.merge_device(order, h.SUBSET_TRAINING, world, RANK_SIZE, d_all.data_ptr(), d_final.data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+
+    # ---- timed region: K steps, CUDA events per step, L2 flushed between steps ----
+    sampler = ClockSampler(local_rank)
+    launches0 = eng.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    search_ms = []
+    barrier()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)                 # > L2 (126 MB): next step starts with a cold L2
+        ev[k][0].record(stream)
+        step_device()
+        ev[k][1].record(stream)
+        ms, grid = eng.last_search_ms()
+        search_ms.append(ms)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = eng.launch_count - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    value = total * F * args.steps / (dev_ms * 1e-3)
+
+    # ---- e2e: host buffers in, host result out ----
+    for _ in range(2):
+        eng.run_host(g, A, U, F, fos, order, h.SUBSET_TRAINING, RANK_SIZE, first, last, out=h_out)
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.run_host(g, A, U, F, fos, order, h.SUBSET_TRAINING, RANK_SIZE, first, last, out=h_out)
+        if world > 1:
+            d_local.copy_(torch.from_numpy(h_out.view(np.uint8).reshape(-1)), non_blocking=False)
+            dist.all_gather_into_tensor(d_all, d_local)
+            eng.merge_device(order, h.SUBSET_TRAINING, world, RANK_SIZE, d_all.data_ptr(), d_final.data_ptr())
+            d_final.cpu()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = total * F * e2e_steps / float(t.item())
+    lay = eng.layout()
+
+    # ---- roofline of the dominant kernel (rank 0's shard) ----
+    my_combs = last - first
+    Wwords = lay["words_per_class_row"]
+    popc_per_comb = (3 ** order) * Wwords                 # algorithmic POPC32 per combination, all folds together
+    k_ms = float(np.mean(search_ms))
+    achieved = my_combs * popc_per_comb / (k_ms * 1e-3)
+    popc_peak = max(eng.pipe_peak(0, 2000), eng.pipe_peak(0, 4000))
+    plane_bytes = lay["plane_bytes"]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    roofline = {
+        "bound": "int_popc", "kernel": f"search{order}_kernel", "achieved": achieved / 1e12, "peak": popc_peak / 1e12, "unit": "TPOPC32/s",
+        "frac": achieved / popc_peak, "traffic": None,
+        "algorithmic": f"3^{order} x W = {popc_per_comb} POPC32 per combination (W = {Wwords} words), {my_combs} combinations per launch",
+        "peak_source": "POPC micro-benchmark in this run (hpgv_epi_pipe_peak), all SMs",
+        "kernel_ms": k_ms, "kernel_share_of_step": k_ms * args.steps / (sum(a.elapsed_time(b) for a, b in ev)),
+        "hbm": {"compulsory_bytes": plane_bytes, "achieved_gbs": plane_bytes / (k_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s", "frac": plane_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak},
+    }
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                cpu = cpu_baseline(g, w)
+            except Exception as e:        # the baseline is a reported figure; never let it kill the bench line
+                cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": f"failed: {e}"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": w["name"] if world == 1 else w["name"] + f" -- weak-scaled to {nv} SNPs for {world} GPUs",
+                       "order": order, "num_variants": nv, "num_affected": A, "num_unaffected": U, "num_folds": F,
+                       "rank_size": RANK_SIZE, "eval_subset": "training", "combinations": total,
+                       "sharding": f"{world} contiguous combination-index ranges", "l2": "flushed between timed steps (256 MiB write)",
+                       "layout": lay},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nv * S + lay["num_blocks"] * lay["block_words"] * 32 * 4),
+                    "d2h_bytes_per_step": rec_bytes, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "wall_s_timed_region": t_wall,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

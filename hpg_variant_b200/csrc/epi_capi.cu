@@ -89,6 +89,10 @@ struct hpgv_epi_ctx {
     int64_t wl_nv = -1;
     int wl_it0 = 0, wl_nit = 0;
     int64_t wl_units = 0;
+    // device-side timing of the dominant kernel (bench.py's roofline): events around every search launch
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+    int last_grid = 0;
 };
 
 #define CK(call)                                                                                   \
@@ -151,6 +155,8 @@ extern "C" int hpgv_epi_create(int device, hpgv_epi_ctx **out) {
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
     ctx->max_smem_optin = (int) prop.sharedMemPerBlockOptin;
+    cudaEventCreate(&ctx->ev0);
+    cudaEventCreate(&ctx->ev1);
     *out = ctx;
     return HPGV_OK;
 }
@@ -161,6 +167,8 @@ extern "C" void hpgv_epi_destroy(hpgv_epi_ctx *ctx) {
     ctx->raw_owned.release(); ctx->d_fl.release(); ctx->d_perm.release(); ctx->d_blk.release(); ctx->d_planes.release();
     ctx->d_lists.release(); ctx->d_list_cnt.release(); ctx->d_gthr.release(); ctx->d_counter.release();
     ctx->d_prefix.release(); ctx->d_jt0.release(); ctx->d_sel.release(); ctx->d_out.release(); ctx->d_merge_in.release();
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     delete ctx;
 }
 
@@ -486,8 +494,12 @@ static int launch_search(hpgv_epi_ctx *ctx, K kernel, size_t smem, SearchArgs &a
     args.unit_counter = ctx->d_counter.p;
     reset_search_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_counter.p, ctx->d_gthr.p);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
     kernel<<<(unsigned) grid, kSearchThreads, smem, ctx->stream>>>(args);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->ev_valid = true;
+    ctx->last_grid = (int) grid;
     ctx->launches += 2;
 
     CK(ctx->d_sel.reserve((size_t) F * grid * rank));   // scratch of the merge that follows
@@ -682,6 +694,15 @@ extern "C" int hpgv_epi_run_host(hpgv_epi_ctx *ctx, const uint8_t *genotypes, in
     rc = hpgv_epi_set_folds(ctx, F, fold_of_sample);
     if (rc) return rc;
     return hpgv_epi_search(ctx, order, eval_subset, rank, first, last, out);
+}
+
+extern "C" int hpgv_epi_last_search_ms(hpgv_epi_ctx *ctx, float *ms, int *grid) {
+    if (!ctx || !ms) return HPGV_E_ARG;
+    if (!ctx->ev_valid) FAIL(HPGV_E_STATE, "no search has been launched yet");
+    CK(cudaEventSynchronize(ctx->ev1));
+    CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    if (grid) *grid = ctx->last_grid;
+    return HPGV_OK;
 }
 
 extern "C" int hpgv_epi_layout(const hpgv_epi_ctx *ctx, hpgv_epi_layout_t *out) {

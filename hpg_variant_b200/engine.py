@@ -124,6 +124,11 @@ class EpistasisEngine:
         self._ck(self.lib.hpgv_epi_unpack_masks(self.h, int(variant), _ptr(out)))
         return out
 
+    def last_search_ms(self):
+        ms, grid = C.c_float(), C.c_int()
+        self._ck(self.lib.hpgv_epi_last_search_ms(self.h, C.byref(ms), C.byref(grid)))
+        return ms.value, grid.value
+
     def pipe_peak(self, kind, iters=2000):
         v = C.c_double()
         self._ck(self.lib.hpgv_epi_pipe_peak(self.h, kind, iters, C.byref(v)))

@@ -153,6 +153,10 @@ typedef struct {
 } hpgv_epi_layout_t;
 int hpgv_epi_layout(const hpgv_epi_ctx *ctx, hpgv_epi_layout_t *out);
 
+/* Device time (CUDA events on the context's stream) of the most recent search kernel launch --
+ * the dominant kernel -- and its grid size.  Blocks until that launch has finished. */
+int hpgv_epi_last_search_ms(hpgv_epi_ctx *ctx, float *ms, int *grid);
+
 /* POPC / LOP3 pipe micro-benchmark (roofline denominator):
  * runs `iters` dependent-free rounds per thread on every SM and returns
  * measured 32-bit ops per second.  kind: 0 = POPC, 1 = LOP3, 2 = POPC+LOP3 mix. */
