@@ -102,32 +102,38 @@ __device__ __forceinline__ void warp_offer(SearchCtl *ctl, const SearchArgs &a, 
     __syncwarp();
     __threadfence_block();
     Cand *list = a.lists + ((size_t) blockIdx.x * ctl->fl.F + f) * a.rank;
-    int cnt = *reinterpret_cast<volatile int *>(&ctl->cnt[f]);
-    bool rescan = false;
+    // every lane reads the list state BEFORE lane 0 modifies it, so the decisions below are warp-uniform
+    const int cnt = *reinterpret_cast<volatile int *>(&ctl->cnt[f]);
+    bool replace = false;
+    int mi = 0;
+    if (cnt >= a.rank) {
+        mi = *reinterpret_cast<volatile int *>(&ctl->min_idx[f]);
+        const Cand worst = cand_load(list + mi);
+        replace = cand_before(c, worst);
+    }
+    __syncwarp();
+    bool rescan;
     if (cnt < a.rank) {
         if (lane == 0) {
             cand_store(list + cnt, c);
             *reinterpret_cast<volatile int *>(&ctl->cnt[f]) = cnt + 1;
         }
-        cnt++;
-        rescan = (cnt == a.rank);
+        rescan = (cnt + 1 == a.rank);
     } else {
-        const int mi = *reinterpret_cast<volatile int *>(&ctl->min_idx[f]);
-        Cand worst = cand_load(list + mi);
-        if (cand_before(c, worst)) {
-            if (lane == 0) cand_store(list + mi, c);
-            rescan = true;
-        }
+        if (replace && lane == 0) cand_store(list + mi, c);
+        rescan = replace;
     }
     __syncwarp();
     if (rescan) {
         // list is full: find the entry that ranks last; its score is the new threshold
         __threadfence_block();
+        // sentinel that ranks before every real entry, so lanes without an entry never win
         Cand w;
+        w.ba = INFINITY; w.i = -1; w.j = -1; w.k = -1; w.mask = 0; w.tp = 0; w.fp = 0;
         int widx = -1;
         for (int e = lane; e < a.rank; e += 32) {
             Cand x = cand_load(list + e);
-            if (widx < 0 || cand_before(w, x)) { w = x; widx = e; }
+            if (cand_before(w, x)) { w = x; widx = e; }
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
@@ -138,8 +144,9 @@ __device__ __forceinline__ void warp_offer(SearchCtl *ctl, const SearchArgs &a, 
             o.k = __shfl_xor_sync(0xffffffffu, w.k, off);
             o.tp = __shfl_xor_sync(0xffffffffu, w.tp, off);
             o.fp = __shfl_xor_sync(0xffffffffu, w.fp, off);
-            int oidx = __shfl_xor_sync(0xffffffffu, widx, off);
-            if (oidx >= 0 && (widx < 0 || cand_before(w, o))) { w = o; widx = oidx; }
+            o.mask = 0;
+            const int oidx = __shfl_xor_sync(0xffffffffu, widx, off);
+            if (cand_before(w, o)) { w = o; widx = oidx; }
         }
         if (lane == 0) {
             const FoldLayout &fl = ctl->fl;
