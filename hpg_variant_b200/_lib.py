@@ -17,7 +17,8 @@ UINT64_MAX = (1 << 64) - 1
 
 class Layout(C.Structure):
     _fields_ = [("num_folds", C.c_int), ("num_segments", C.c_int), ("num_blocks", C.c_int), ("block_words", C.c_int),
-                ("count_bits", C.c_int), ("plane_bytes", C.c_int64), ("words_per_class_row", C.c_int)]
+                ("count_bits", C.c_int), ("plane_bytes", C.c_int64), ("words_per_class_row", C.c_int),
+                ("num_chunks", C.c_int), ("chunk_blocks", C.c_int), ("row_words", C.c_int)]
 
 
 class HpgvError(RuntimeError):

@@ -61,8 +61,6 @@ struct hpgv_epi_ctx {
     // fold layout + packed planes
     bool folds_set = false;
     FoldLayout fl{};
-    int cbits = 8;
-    bool single = true;
     int64_t snp_pad = 0;
     int64_t npos = 0;                     // bit positions per SNP row = nblocks * bw * 32
     std::vector<int32_t> perm;
@@ -77,10 +75,8 @@ struct hpgv_epi_ctx {
     DevBuf<Cand> d_lists;
     DevBuf<int> d_list_cnt;
     DevBuf<long long> d_gthr;
-    DevBuf<unsigned long long> d_counter;
     DevBuf<int64_t> d_prefix;
     DevBuf<int32_t> d_jt0;
-    DevBuf<int> d_sel;
     DevBuf<hpgv_epi_model_t> d_out;
     DevBuf<Cand> d_merge_in;
     // cached work list
@@ -111,10 +107,9 @@ struct hpgv_epi_ctx {
     } while (0)
 
 // ---------------------------------------------------------------------------------
-// reset kernel: work counter and global thresholds
+// reset kernel: global thresholds
 // ---------------------------------------------------------------------------------
-__global__ void reset_search_kernel(unsigned long long *counter, long long *gthr) {
-    if (threadIdx.x == 0) *counter = 0ULL;
+__global__ void reset_search_kernel(long long *gthr) {
     if (threadIdx.x < kMaxFolds) gthr[threadIdx.x] = LLONG_MIN;
 }
 
@@ -165,8 +160,8 @@ extern "C" void hpgv_epi_destroy(hpgv_epi_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     ctx->raw_owned.release(); ctx->d_fl.release(); ctx->d_perm.release(); ctx->d_blk.release(); ctx->d_planes.release();
-    ctx->d_lists.release(); ctx->d_list_cnt.release(); ctx->d_gthr.release(); ctx->d_counter.release();
-    ctx->d_prefix.release(); ctx->d_jt0.release(); ctx->d_sel.release(); ctx->d_out.release(); ctx->d_merge_in.release();
+    ctx->d_lists.release(); ctx->d_list_cnt.release(); ctx->d_gthr.release();
+    ctx->d_prefix.release(); ctx->d_jt0.release(); ctx->d_out.release(); ctx->d_merge_in.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     delete ctx;
@@ -285,23 +280,38 @@ extern "C" int hpgv_epi_set_folds(hpgv_epi_ctx *ctx, int F, const int32_t *fold_
     }
     if (max_seg > 65535) FAIL(HPGV_E_UNSUPPORTED, "more than 65535 samples of one class in one fold");
     if ((long long) A * U >= (1LL << 62)) FAIL(HPGV_E_UNSUPPORTED, "cohort too large");
+    // Layout: a segment is one block when it fits 4 or 8 words (byte counters), else a run of 8-word blocks.
+    fl.single = max_seg <= 255;
     fl.bw = max_seg <= 128 ? 4 : 8;
-    ctx->cbits = max_seg <= 255 ? 8 : 16;
     const int bits_per_block = 32 * fl.bw;
     std::vector<int> seg_blocks(2 * F), seg_first(2 * F);
     int nb = 0;
     for (int s = 0; s < 2 * F; s++) {
-        seg_blocks[s] = std::max(1, (seg_size[s] + bits_per_block - 1) / bits_per_block);
+        seg_blocks[s] = fl.single ? 1 : std::max(1, (seg_size[s] + bits_per_block - 1) / bits_per_block);
         seg_first[s] = nb;
         nb += seg_blocks[s];
     }
-    if (nb > kMaxBlocks) FAIL(HPGV_E_UNSUPPORTED, "sample axis needs more than 8192 blocks");
+    const int nb_real = nb;
+    if (fl.single) nb = (nb + 3) / 4 * 4;              // byte counters are packed four blocks to a word
+    if (nb > kMaxBlocks) FAIL(HPGV_E_UNSUPPORTED, "sample axis needs more than 4096 blocks (1M samples)");
     fl.nblocks = nb;
-    ctx->single = (nb == 2 * F);
-    ctx->blk.assign(nb, 0);
+    // chunks: a stage of the search kernels holds (16 + 32 + 1) chunk rows; keep it within 48 KB
+    {
+        const int block_bytes = 3 * fl.bw * 4;
+        int cb_max = std::max(1, (48 * 1024 / (kMaxWarps + kTileJ + 1) - 16) / block_bytes);
+        if (fl.single) cb_max = std::max(4, cb_max / 4 * 4);
+        fl.nchunks = (nb + cb_max - 1) / cb_max;
+        fl.cb = (nb + fl.nchunks - 1) / fl.nchunks;
+        if (fl.single) fl.cb = (fl.cb + 3) / 4 * 4;
+        fl.nchunks = (nb + fl.cb - 1) / fl.cb;
+        fl.row_words = fl.cb * 3 * fl.bw;
+        if ((fl.row_words / 4) % 2 == 0) fl.row_words += 4;   // odd number of 16-byte groups per row: conflict-free LDS.128
+    }
+    ctx->blk.assign(nb, (uint16_t) 0x7fff);            // padding blocks belong to no segment
     for (int s = 0; s < 2 * F; s++)
         for (int b = 0; b < seg_blocks[s]; b++)
             ctx->blk[seg_first[s] + b] = (uint16_t) (s | (b == seg_blocks[s] - 1 ? 0x8000 : 0));
+    (void) nb_real;
     ctx->npos = (int64_t) nb * bits_per_block;
     ctx->perm.assign((size_t) ctx->npos, -1);
     {
@@ -314,7 +324,7 @@ extern "C" int hpgv_epi_set_folds(hpgv_epi_ctx *ctx, int F, const int32_t *fold_
     ctx->fl = fl;
     // rows are padded so that every tile a kernel stages (<= 32 rows past any valid origin) stays inside the buffer
     ctx->snp_pad = ((ctx->nv + kTileJ - 1) / kTileJ) * kTileJ + kTileJ;
-    ctx->plane_words = (size_t) nb * (size_t) ctx->snp_pad * 3 * fl.bw;
+    ctx->plane_words = (size_t) fl.nchunks * (size_t) ctx->snp_pad * fl.row_words;
 
     CK(ctx->d_fl.reserve(1));
     CK(ctx->d_perm.reserve(ctx->perm.size()));
@@ -329,10 +339,7 @@ extern "C" int hpgv_epi_set_folds(hpgv_epi_ctx *ctx, int F, const int32_t *fold_
     const int threads = 256;
     const int64_t blocks = (warps * 32 + threads - 1) / threads;
     if (blocks > INT32_MAX) FAIL(HPGV_E_UNSUPPORTED, "dataset too large for the packer grid");
-    if (fl.bw == 4)
-        pack_planes_kernel<4><<<(unsigned) blocks, threads, 0, ctx->stream>>>(ctx->d_raw, ctx->nv, S, ctx->d_perm.p, nb, ctx->snp_pad, ctx->d_planes.p);
-    else
-        pack_planes_kernel<8><<<(unsigned) blocks, threads, 0, ctx->stream>>>(ctx->d_raw, ctx->nv, S, ctx->d_perm.p, nb, ctx->snp_pad, ctx->d_planes.p);
+    pack_planes_kernel<<<(unsigned) blocks, threads, 0, ctx->stream>>>(ctx->d_raw, ctx->nv, S, ctx->d_perm.p, ctx->d_fl.p, ctx->snp_pad, ctx->d_planes.p);
     CK(cudaGetLastError());
     ctx->launches++;
     // perm/blk host vectors are read by the async copies above
@@ -418,8 +425,6 @@ cudaError_t opt_in_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
 }
 
-size_t ctl_bytes() { return ((sizeof(SearchCtl) + 127) / 128) * 128; }
-
 }  // namespace
 
 static int build_worklist(hpgv_epi_ctx *ctx, int order, int ti, uint64_t first, uint64_t last) {
@@ -449,8 +454,8 @@ static int build_worklist(hpgv_epi_ctx *ctx, int order, int ti, uint64_t first, 
                 else jt0.push_back(0);
             }
         } else {
-            // super-unit = (row i, tile of kConsumerWarps j rows); the producer walks the k tiles
-            const int tj = kConsumerWarps;
+            // unit = (row i, tile of `ti` j rows, one per warp); the CTA walks the k tiles itself
+            const int tj = ti;
             const int64_t i_first = unrank_triple_first((uint64_t) nv, first);
             const int64_t i_last = unrank_triple_first((uint64_t) nv, last - 1);
             it0 = (int) i_first;
@@ -473,37 +478,62 @@ static int build_worklist(hpgv_epi_ctx *ctx, int order, int ti, uint64_t first, 
     return HPGV_OK;
 }
 
+// Picks the CTA size (16, 8, 4, 2 or 1 warps = tile rows) that fits shared memory, and whether the per-CTA top-N
+// lists can live in shared memory during the search.
+struct SearchShape {
+    int nthreads = 0;
+    bool lists_in_smem = false;
+    size_t smem = 0;
+};
+static SearchShape pick_shape(const hpgv_epi_ctx *ctx, int order, int rank) {
+    const FoldLayout &fl = ctx->fl;
+    const int ncells = order == 2 ? 9 : 27;
+    SearchShape best;
+    for (int warps = kMaxWarps; warps >= 1; warps >>= 1) {
+        const int rows = order == 2 ? warps + kTileJ : 1 + warps + kTileJ;
+        for (int in_smem = 1; in_smem >= 0; in_smem--) {
+            if (in_smem && (size_t) fl.F * rank * sizeof(Cand) > 24 * 1024) continue;
+            const SmemMap m = search_smem_map(fl, rows, ncells, warps * 32, rank, in_smem != 0);
+            if (m.total <= (size_t) ctx->max_smem_optin) {
+                best.nthreads = warps * 32; best.lists_in_smem = in_smem != 0; best.smem = m.total;
+                return best;
+            }
+        }
+    }
+    return best;
+}
+
 template <typename K>
-static int launch_search(hpgv_epi_ctx *ctx, K kernel, size_t smem, SearchArgs &args, int F, int rank) {
-    if (smem > (size_t) ctx->max_smem_optin)
-        FAIL(HPGV_E_UNSUPPORTED, "fold count x cell count needs " + std::to_string(smem) + " bytes of shared memory per CTA (limit " +
-                                     std::to_string(ctx->max_smem_optin) + ")");
-    CK(opt_in_smem(kernel, smem));
-    int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kSearchThreads, smem));
-    if (per_sm < 1) FAIL(HPGV_E_UNSUPPORTED, "search kernel does not fit on an SM");
-    int64_t grid = (int64_t) per_sm * ctx->num_sms;
+static int launch_search(hpgv_epi_ctx *ctx, K kernel, const SearchShape &shape, SearchArgs &args, int F, int rank) {
+    CK(opt_in_smem(kernel, shape.smem));
+    int64_t grid = ctx->num_sms;                       // one persistent CTA per SM
     grid = std::max<int64_t>(1, std::min<int64_t>(grid, std::max<int64_t>(args.num_units, 1)));
     CK(ctx->d_lists.reserve((size_t) grid * F * rank));
     CK(ctx->d_list_cnt.reserve((size_t) grid * F));
     CK(ctx->d_gthr.reserve(kMaxFolds));
-    CK(ctx->d_counter.reserve(1));
     args.lists = ctx->d_lists.p;
     args.list_cnt = ctx->d_list_cnt.p;
     args.gthr = ctx->d_gthr.p;
-    args.unit_counter = ctx->d_counter.p;
-    reset_search_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_counter.p, ctx->d_gthr.p);
+    args.lists_in_smem = shape.lists_in_smem ? 1 : 0;
+    reset_search_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_gthr.p);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    kernel<<<(unsigned) grid, kSearchThreads, smem, ctx->stream>>>(args);
+    kernel<<<(unsigned) grid, shape.nthreads, shape.smem, ctx->stream>>>(args);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->ev_valid = true;
     ctx->last_grid = (int) grid;
     ctx->launches += 2;
-
-    CK(ctx->d_sel.reserve((size_t) F * grid * rank));   // scratch of the merge that follows
     return (int) grid;
+}
+
+static int launch_merge(hpgv_epi_ctx *ctx, const MergeArgs &m) {
+    const size_t smem = (size_t) m.rank_out * 20 + 16;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    merge_kernel<<<m.F, kMergeThreads, smem, ctx->stream>>>(m);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return HPGV_OK;
 }
 
 static int do_search(hpgv_epi_ctx *ctx, int order, int eval_subset, int rank, uint64_t first, uint64_t last,
@@ -513,6 +543,7 @@ static int do_search(hpgv_epi_ctx *ctx, int order, int eval_subset, int rank, ui
     if (rank < 1 || rank > kMaxRank) FAIL(HPGV_E_ARG, "rank_size must be in [1, 4096]");
     if (eval_subset != HPGV_SUBSET_TESTING && eval_subset != HPGV_SUBSET_TRAINING) FAIL(HPGV_E_ARG, "eval_subset must be 0 (testing) or 1 (training)");
     if (ctx->nv < order) FAIL(HPGV_E_ARG, "fewer variants than the order");
+    if (order == 3 && ctx->nv >= (1 << 21)) FAIL(HPGV_E_UNSUPPORTED, "order 3 supports fewer than 2^21 variants");
     CK(cudaSetDevice(ctx->device));
     const uint64_t total = hpgv_epi_num_combinations(ctx->nv, order);
     if (last > total) last = total;
@@ -520,7 +551,6 @@ static int do_search(hpgv_epi_ctx *ctx, int order, int eval_subset, int rank, ui
 
     const FoldLayout &fl = ctx->fl;
     const int F = fl.F;
-    const int nwc = words_per_cell(fl.nseg, ctx->cbits);
     SearchArgs args{};
     args.planes = ctx->d_planes.p;
     args.blk_desc = ctx->d_blk.p;
@@ -532,9 +562,10 @@ static int do_search(hpgv_epi_ctx *ctx, int order, int eval_subset, int rank, ui
     args.first = first;
     args.last = last;
 
-    const int ppt = (order == 2) ? (ctx->cbits == 8 ? 2 : 1) : 1;
-    const int ti = (order == 2) ? kConsumerWarps * ppt : 1;
-    int rc = build_worklist(ctx, order, ti, first, last);
+    const SearchShape shape = pick_shape(ctx, order, rank);
+    if (shape.nthreads == 0)
+        FAIL(HPGV_E_UNSUPPORTED, "fold count x cell count does not fit the shared memory of an SM (" + std::to_string(ctx->max_smem_optin) + " bytes)");
+    int rc = build_worklist(ctx, order, shape.nthreads / 32, first, last);
     if (rc) return rc;
     args.unit_prefix = ctx->d_prefix.p;
     args.unit_jt0 = ctx->d_jt0.p;
@@ -542,31 +573,28 @@ static int do_search(hpgv_epi_ctx *ctx, int order, int eval_subset, int rank, ui
     args.n_it = ctx->wl_nit;
     args.num_units = ctx->wl_units;
 
+    // the packed-pair epilogue needs A == U (r = 1: the float32 rule is exact) and 16-bit class sizes
+    const bool balanced = fl.balanced && fl.A <= 65535;
     int grid = 0;
-    if (order == 2) {
-        const size_t stage_bytes = (size_t) kStages * (ti + kTileJ) * 3 * fl.bw * 4;
-        const size_t smem = ctl_bytes() + stage_bytes + (size_t) ppt * 9 * nwc * kConsumers * 4;
-        if (fl.bw == 4) grid = launch_search(ctx, search2_kernel<4, 8, 2, true>, smem, args, F, rank);
-        else if (ctx->cbits == 8) grid = launch_search(ctx, search2_kernel<8, 8, 2, true>, smem, args, F, rank);
-        else grid = launch_search(ctx, search2_kernel<8, 16, 1, false>, smem, args, F, rank);
-    } else {
-        const size_t rows = 1 + kConsumerWarps + kTileJ;
-        const size_t stagew = ((rows * 3 * fl.bw + 3) / 4) * 4;
-        const size_t smem = ctl_bytes() + (size_t) kStages * stagew * 4 + (size_t) 27 * nwc * kConsumers * 4;
-        if (fl.bw == 4) grid = launch_search(ctx, search3_kernel<4, 8, true>, smem, args, F, rank);
-        else if (ctx->cbits == 8) grid = launch_search(ctx, search3_kernel<8, 8, true>, smem, args, F, rank);
-        else grid = launch_search(ctx, search3_kernel<8, 16, false>, smem, args, F, rank);
-    }
+#define HPGV_LAUNCH(KERNEL)                                                                          \
+    do {                                                                                             \
+        if (fl.bw == 4) grid = balanced ? launch_search(ctx, KERNEL<4, true, true>, shape, args, F, rank)    \
+                                        : launch_search(ctx, KERNEL<4, true, false>, shape, args, F, rank);  \
+        else if (fl.single) grid = balanced ? launch_search(ctx, KERNEL<8, true, true>, shape, args, F, rank)    \
+                                            : launch_search(ctx, KERNEL<8, true, false>, shape, args, F, rank);  \
+        else grid = balanced ? launch_search(ctx, KERNEL<8, false, true>, shape, args, F, rank)      \
+                             : launch_search(ctx, KERNEL<8, false, false>, shape, args, F, rank);    \
+    } while (0)
+    if (order == 2) HPGV_LAUNCH(search2_kernel);
+    else HPGV_LAUNCH(search3_kernel);
+#undef HPGV_LAUNCH
     if (grid < 0) return grid;
 
     MergeArgs m{};
-    m.lists = ctx->d_lists.p; m.list_cnt = ctx->d_list_cnt.p; m.gthr = ctx->d_gthr.p;
+    m.lists = ctx->d_lists.p; m.list_cnt = ctx->d_list_cnt.p;
     m.nlists = grid; m.F = F; m.rank_in = rank; m.rank_out = rank; m.training = args.training;
-    m.fl = ctx->d_fl.p; m.out = d_out; m.order = order; m.sel = ctx->d_sel.p;
-    merge_kernel<<<F, 1024, 0, ctx->stream>>>(m);
-    CK(cudaGetLastError());
-    ctx->launches++;
-    return HPGV_OK;
+    m.fl = ctx->d_fl.p; m.out = d_out; m.order = order;
+    return launch_merge(ctx, m);
 }
 
 extern "C" int hpgv_epi_search_device(hpgv_epi_ctx *ctx, int order, int eval_subset, int rank, uint64_t first, uint64_t last,
@@ -596,21 +624,19 @@ extern "C" int hpgv_epi_merge_device(hpgv_epi_ctx *ctx, int order, int eval_subs
     if (!ctx->folds_set) FAIL(HPGV_E_STATE, "merge before set_folds (fold sizes are needed)");
     if (F != ctx->fl.F) FAIL(HPGV_E_ARG, "num_folds differs from the layout set by set_folds");
     if (num_lists < 1 || rank < 1 || rank > kMaxRank) FAIL(HPGV_E_ARG, "bad list shape");
+    if (order != 2 && order != 3) FAIL(HPGV_E_ARG, "order must be 2 or 3");
     CK(cudaSetDevice(ctx->device));
     const int64_t n = (int64_t) num_lists * F * rank;
     CK(ctx->d_merge_in.reserve((size_t) n));
-    CK(ctx->d_sel.reserve((size_t) n));
     models_to_cands_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const ModelOut *>(d_lists), n, ctx->d_merge_in.p);
     CK(cudaGetLastError());
+    ctx->launches++;
     MergeArgs m{};
-    m.lists = ctx->d_merge_in.p; m.list_cnt = nullptr; m.gthr = nullptr;
+    m.lists = ctx->d_merge_in.p; m.list_cnt = nullptr;
     m.nlists = num_lists; m.F = F; m.rank_in = rank; m.rank_out = rank;
     m.training = (eval_subset == HPGV_SUBSET_TRAINING);
-    m.fl = ctx->d_fl.p; m.out = d_out; m.order = order; m.sel = ctx->d_sel.p;
-    merge_kernel<<<F, 1024, 0, ctx->stream>>>(m);
-    CK(cudaGetLastError());
-    ctx->launches += 2;
-    return HPGV_OK;
+    m.fl = ctx->d_fl.p; m.out = d_out; m.order = order;
+    return launch_merge(ctx, m);
 }
 
 // ---------------------------------------------------------------------------------
@@ -647,10 +673,7 @@ extern "C" int hpgv_epi_eval(hpgv_epi_ctx *ctx, int order, int eval_subset, int6
     const size_t smem = (size_t) warps * ctx->fl.nseg * C * sizeof(int);
     const unsigned grid = (unsigned) ((ncomb + warps - 1) / warps);
     const int training = (eval_subset == HPGV_SUBSET_TRAINING);
-    if (ctx->fl.bw == 4)
-        eval_kernel<4><<<grid, warps * 32, smem, ctx->stream>>>(ctx->d_planes.p, ctx->d_blk.p, ctx->d_fl.p, ctx->snp_pad, order, training, ncomb, d_combs, d_ca, d_cu, d_mask, d_conf, d_acc);
-    else
-        eval_kernel<8><<<grid, warps * 32, smem, ctx->stream>>>(ctx->d_planes.p, ctx->d_blk.p, ctx->d_fl.p, ctx->snp_pad, order, training, ncomb, d_combs, d_ca, d_cu, d_mask, d_conf, d_acc);
+    eval_kernel<<<grid, warps * 32, smem, ctx->stream>>>(ctx->d_planes.p, ctx->d_blk.p, ctx->d_fl.p, ctx->snp_pad, order, training, ncomb, d_combs, d_ca, d_cu, d_mask, d_conf, d_acc);
     CKE(cudaGetLastError());
     ctx->launches++;
     if (counts_aff) CKE(cudaMemcpyAsync(counts_aff, d_ca, nf * C * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -674,10 +697,7 @@ extern "C" int hpgv_epi_unpack_masks(hpgv_epi_ctx *ctx, int64_t variant, uint8_t
     CK(cudaMalloc(&d_out, (size_t) 3 * s_pad));
     cudaMemsetAsync(d_out, 0, (size_t) 3 * s_pad, ctx->stream);
     const unsigned grid = (unsigned) ((ctx->npos + 255) / 256);
-    if (ctx->fl.bw == 4)
-        unpack_masks_kernel<4><<<grid, 256, 0, ctx->stream>>>(ctx->d_planes.p, variant, ctx->snp_pad, ctx->d_perm.p, ctx->npos, ctx->A, a_pad, s_pad, d_out);
-    else
-        unpack_masks_kernel<8><<<grid, 256, 0, ctx->stream>>>(ctx->d_planes.p, variant, ctx->snp_pad, ctx->d_perm.p, ctx->npos, ctx->A, a_pad, s_pad, d_out);
+    unpack_masks_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_planes.p, variant, ctx->snp_pad, ctx->d_perm.p, ctx->d_fl.p, ctx->npos, ctx->A, a_pad, s_pad, d_out);
     ctx->launches++;
     cudaError_t e = cudaMemcpyAsync(out, d_out, (size_t) 3 * s_pad, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -709,7 +729,8 @@ extern "C" int hpgv_epi_layout(const hpgv_epi_ctx *ctx, hpgv_epi_layout_t *out) 
     if (!ctx || !out) return HPGV_E_ARG;
     if (!ctx->folds_set) return HPGV_E_STATE;
     out->num_folds = ctx->fl.F; out->num_segments = ctx->fl.nseg; out->num_blocks = ctx->fl.nblocks; out->block_words = ctx->fl.bw;
-    out->count_bits = ctx->cbits;
+    out->num_chunks = ctx->fl.nchunks; out->chunk_blocks = ctx->fl.cb; out->row_words = ctx->fl.row_words;
+    out->count_bits = ctx->fl.single ? 8 : 16;
     out->plane_bytes = (int64_t) ctx->plane_words * 4;
     out->words_per_class_row = (ctx->A + 31) / 32 + (ctx->U + 31) / 32;
     return HPGV_OK;

@@ -21,22 +21,24 @@ __device__ __forceinline__ void mbar_fence_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
 }
 // global -> shared, completion signalled on an mbarrier (complete_tx::bytes)
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
@@ -46,7 +48,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 }
 
 // ----------------------------------------------------------------------------
-// bit counting: AND the planes, compress with carry-save adders (LOP3), POPC
+// bit counting: AND the planes, compress with carry-save adders (LOP3 on the
+// ALU pipe), POPC (XU pipe) the compressed words, weight and accumulate with
+// IMAD (FMA pipe).  Per block of BW words: BW=4 -> 3 POPC, BW=8 -> 4 POPC.
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t d;
@@ -63,55 +67,68 @@ __device__ __forceinline__ uint32_t and3(uint32_t a, uint32_t b, uint32_t c) {
     asm("lop3.b32 %0, %1, %2, %3, 0x80;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+// acc + v * K with K a compile-time constant (kept as IMAD so that it issues on the FMA pipe, not the ALU)
+template <uint32_t K>
+__device__ __forceinline__ uint32_t mad_const(uint32_t v, uint32_t acc) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(v), "n"(K), "r"(acc));
+    return d;
+}
 
-// number of set bits in x[0..BW): 4 words -> CSA(3)+1 (3 POPC), 8 words -> CSA tree of 7 + 1 (4 POPC)
-template <int BW>
-__device__ __forceinline__ uint32_t count_words(const uint32_t (&x)[BW]) {
+// acc += K * (number of set bits in x[0..BW))
+template <int BW, uint32_t K>
+__device__ __forceinline__ uint32_t count_words_acc(const uint32_t (&x)[BW], uint32_t acc) {
     if constexpr (BW == 4) {
-        uint32_t ones = xor3(x[0], x[1], x[2]);
-        uint32_t twos = maj3(x[0], x[1], x[2]);
-        return __popc(ones) + __popc(x[3]) + 2u * __popc(twos);
+        const uint32_t ones = xor3(x[0], x[1], x[2]);
+        const uint32_t twos = maj3(x[0], x[1], x[2]);
+        acc = mad_const<K>(__popc(ones), acc);
+        acc = mad_const<K>(__popc(x[3]), acc);
+        acc = mad_const<2 * K>(__popc(twos), acc);
+        return acc;
     } else {
         static_assert(BW == 8, "block width must be 4 or 8 words");
-        uint32_t s1 = xor3(x[0], x[1], x[2]), c1 = maj3(x[0], x[1], x[2]);
-        uint32_t s2 = xor3(x[3], x[4], x[5]), c2 = maj3(x[3], x[4], x[5]);
-        uint32_t s3 = xor3(s1, s2, x[6]),     c3 = maj3(s1, s2, x[6]);
-        uint32_t t  = xor3(c1, c2, c3),       f  = maj3(c1, c2, c3);
-        return __popc(s3) + __popc(x[7]) + 2u * __popc(t) + 4u * __popc(f);
+        const uint32_t s1 = xor3(x[0], x[1], x[2]), c1 = maj3(x[0], x[1], x[2]);
+        const uint32_t s2 = xor3(x[3], x[4], x[5]), c2 = maj3(x[3], x[4], x[5]);
+        const uint32_t s3 = xor3(s1, s2, x[6]),     c3 = maj3(s1, s2, x[6]);
+        const uint32_t t  = xor3(c1, c2, c3),       f  = maj3(c1, c2, c3);
+        acc = mad_const<K>(__popc(s3), acc);
+        acc = mad_const<K>(__popc(x[7]), acc);
+        acc = mad_const<2 * K>(__popc(t), acc);
+        acc = mad_const<4 * K>(__popc(f), acc);
+        return acc;
     }
 }
 
-template <int BW>
-__device__ __forceinline__ uint32_t cell_count2(const uint32_t (&a)[BW], const uint32_t (&b)[BW]) {
+template <int BW, uint32_t K>
+__device__ __forceinline__ uint32_t cell_count2_acc(const uint32_t (&a)[BW], const uint32_t (&b)[BW], uint32_t acc) {
     uint32_t x[BW];
 #pragma unroll
     for (int w = 0; w < BW; w++) x[w] = a[w] & b[w];
-    return count_words<BW>(x);
+    return count_words_acc<BW, K>(x, acc);
 }
-template <int BW>
-__device__ __forceinline__ uint32_t cell_count3(const uint32_t (&a)[BW], const uint32_t (&b)[BW], const uint32_t (&c)[BW]) {
+template <int BW, uint32_t K>
+__device__ __forceinline__ uint32_t cell_count3_acc(const uint32_t (&a)[BW], const uint32_t (&b)[BW], const uint32_t (&c)[BW], uint32_t acc) {
     uint32_t x[BW];
 #pragma unroll
     for (int w = 0; w < BW; w++) x[w] = and3(a[w], b[w], c[w]);
-    return count_words<BW>(x);
+    return count_words_acc<BW, K>(x, acc);
 }
 
-// One plane (BW words) of a staged row.  For BW == 8 the two 16-byte halves of a
-// plane are stored swapped when bit 2 of the SNP index is set, which makes the
-// per-lane LDS.128 of 32 consecutive rows (96-byte stride) bank-conflict free.
+// One plane (BW words) from a staged row in shared memory (16-byte aligned).
 template <int BW>
-__device__ __forceinline__ void load_plane(const uint32_t *row, int g, int swz, uint32_t (&p)[BW]) {
-    if constexpr (BW == 4) {
-        uint4 v = *reinterpret_cast<const uint4 *>(row + g * 4);
-        p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w;
-    } else {
-        uint4 lo = *reinterpret_cast<const uint4 *>(row + g * 8 + (swz ? 4 : 0));
-        uint4 hi = *reinterpret_cast<const uint4 *>(row + g * 8 + (swz ? 0 : 4));
-        p[0] = lo.x; p[1] = lo.y; p[2] = lo.z; p[3] = lo.w;
-        p[4] = hi.x; p[5] = hi.y; p[6] = hi.z; p[7] = hi.w;
+__device__ __forceinline__ void load_plane(const uint32_t *p, uint32_t (&v)[BW]) {
+#pragma unroll
+    for (int q = 0; q < BW / 4; q++) {
+        const uint4 t = *reinterpret_cast<const uint4 *>(p + 4 * q);
+        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
     }
 }
-__host__ __device__ __forceinline__ int swizzle_of(int64_t snp) { return static_cast<int>((snp >> 2) & 1); }
+
+// word offset of (chunk, snp, block-in-chunk, plane, word) inside the packed planes
+__host__ __device__ __forceinline__ int64_t plane_word(const FoldLayout &fl, int64_t snp_pad, int b, int64_t snp, int g, int w) {
+    const int ch = b / fl.cb, bl = b % fl.cb;
+    return ((int64_t) ch * snp_pad + snp) * fl.row_words + (bl * 3 + g) * fl.bw + w;
+}
 
 // ----------------------------------------------------------------------------
 // High-risk rule -- bit-exact with mdr_high_risk_combinations2 (mdr.c:45-75).
@@ -182,11 +199,12 @@ __device__ __forceinline__ bool cand_before(const Cand &a, const Cand &b) {
     return cand_before(a.ba, a.i, a.j, a.k, b.ba, b.i, b.j, b.k);
 }
 
-// list entries live in global memory and are shared by the warps of one CTA:
-// always go through L2 (ld.cg / st.cg) so no warp sees a stale L1 line.
+// List entries are shared by the warps of one CTA and live either in shared or in
+// global memory: volatile generic accesses never hit a stale L1 line.
 __device__ __forceinline__ Cand cand_load(const Cand *p) {
-    const int4 *q = reinterpret_cast<const int4 *>(p);
-    int4 a = __ldcg(q), b = __ldcg(q + 1);
+    int4 a, b;
+    asm volatile("ld.volatile.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(p));
+    asm volatile("ld.volatile.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(reinterpret_cast<const int4 *>(p) + 1));
     Cand c;
     c.ba = __hiloint2double(a.y, a.x);
     c.i = a.z; c.j = a.w; c.k = b.x; c.mask = (uint32_t) b.y; c.tp = b.z; c.fp = b.w;
@@ -196,9 +214,8 @@ __device__ __forceinline__ void cand_store(Cand *p, const Cand &c) {
     int4 a, b;
     a.x = __double2loint(c.ba); a.y = __double2hiint(c.ba); a.z = c.i; a.w = c.j;
     b.x = c.k; b.y = (int) c.mask; b.z = c.tp; b.w = c.fp;
-    int4 *q = reinterpret_cast<int4 *>(p);
-    __stcg(q, a);
-    __stcg(q + 1, b);
+    asm volatile("st.volatile.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w) : "memory");
+    asm volatile("st.volatile.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(reinterpret_cast<int4 *>(p) + 1), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
 }
 
 // linear index of the pair (i, j), i < j, in lexicographic order over n SNPs

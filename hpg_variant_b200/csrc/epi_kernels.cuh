@@ -6,19 +6,22 @@
 //   merge_kernel         per-CTA / per-rank top-N lists -> final top-N        (replaces the heap drain + MPI tree merge)
 //   eval_kernel          per-combination dump for explicit combinations       (parity hook)
 //
-// Design (DESIGN.md has the long form): a persistent CTA = 1 producer warp +
-// NWARPS consumer warps.  The producer pulls work units from a global counter
-// and streams, block by block along the sample axis, the bit planes of the
-// unit's SNP rows into a shared-memory ring with 1-D bulk async copies
-// (cp.async.bulk -> SASS UBLKCP) completing on mbarriers.  A consumer thread
-// owns PPT SNP combinations (lane <-> last SNP of the tuple, so that row loads
-// are one conflict-free LDS.128 per lane; the other SNPs are warp-uniform
-// broadcast loads), ANDs the planes, compresses with LOP3 carry-save adders
-// and POPCs, and writes one count per (cell, segment) into its private slice of
-// shared memory.  After the last block the thread derives the whole-sample
-// table, the F per-fold training tables (total - in-fold), the exact high-risk
-// masks, TP/FP and an integer score per fold, and offers candidates that beat
-// the running threshold to the CTA's top-N list.
+// Design of the search kernels (DESIGN.md has the long form).  One persistent CTA
+// per SM walks a static round-robin share of the work units.  A unit is a tile of
+// SNP tuples: warp <-> one row of the tile (i for order 2, j for order 3), lane <->
+// the last SNP of the tuple, so the lane's own planes are one conflict-free LDS.128
+// per plane and the other SNPs' planes are warp-uniform broadcast loads.  The sample
+// axis is cut into chunks; for every (unit, chunk) step thread 0 issues two or three
+// 1-D bulk async copies (cp.async.bulk -> SASS UBLKCP) that land the chunk rows of
+// the tile in one of two shared-memory stages and complete on an mbarrier, one step
+// ahead of the compute.  A thread ANDs the planes of its tuple cell by cell,
+// compresses each block with LOP3 carry-save adders (ALU pipe), POPCs the compressed
+// words (XU pipe) and accumulates the weighted counts with IMAD (FMA pipe) straight
+// into packed per-segment counters (four byte counters or two 16-bit counters per
+// word) that go to the thread's private slice of shared memory once per four blocks
+// / once per segment.  After the last chunk the thread derives, per fold, the
+// training table (total - in-fold), the exact high-risk mask, TP/FP and an integer
+// score, and offers tuples that beat the running threshold to the CTA's top-N list.
 #pragma once
 #include "epi_device.cuh"
 
@@ -30,45 +33,40 @@ namespace hpgv {
 // One warp per (snp, block, word): lane l reads the genotype byte of the sample
 // mapped to bit l and three ballots produce the three plane words.
 // perm[pos] = dataset column of the sample at bit position pos, or -1 (padding).
-template <int BW>
 __global__ void pack_planes_kernel(const uint8_t *__restrict__ raw, int64_t nv, int64_t nsamples,
-                                   const int32_t *__restrict__ perm, int nblocks, int64_t snp_pad,
+                                   const int32_t *__restrict__ perm, const FoldLayout *__restrict__ flp, int64_t snp_pad,
                                    uint32_t *__restrict__ planes) {
+    const FoldLayout &fl = *flp;
+    const int bw = fl.bw;
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t words_per_snp = (int64_t) nblocks * BW;
+    const int64_t words_per_snp = (int64_t) fl.nblocks * bw;
     if (warp >= nv * words_per_snp) return;
     const int64_t snp = warp / words_per_snp;
     const int wb = (int) (warp % words_per_snp);
-    const int b = wb / BW, w = wb % BW;
+    const int b = wb / bw, w = wb % bw;
     const int32_t col = perm[(int64_t) wb * 32 + lane];
     const uint32_t g = col >= 0 ? raw[snp * nsamples + col] : 255u;
     const uint32_t m0 = __ballot_sync(0xffffffffu, g == 0);
     const uint32_t m1 = __ballot_sync(0xffffffffu, g == 1);
     const uint32_t m2 = __ballot_sync(0xffffffffu, g == 2);
-    if (lane < 3) {
-        int pos = w;
-        if (BW == 8) pos = (((w >> 2) ^ swizzle_of(snp)) << 2) | (w & 3);
-        planes[(((int64_t) b * snp_pad + snp) * 3 + lane) * BW + pos] = lane == 0 ? m0 : (lane == 1 ? m1 : m2);
-    }
+    if (lane < 3) planes[plane_word(fl, snp_pad, b, snp, lane, w)] = lane == 0 ? m0 : (lane == 1 ? m1 : m2);
 }
 
 // Inverse of the packer for one SNP: byte masks in the reference's layout
-// [genotype][S_pad] (model.c:28-74).  One thread per sample column.
-template <int BW>
+// [genotype][S_pad] (model.c:28-74).  One thread per bit position.
 __global__ void unpack_masks_kernel(const uint32_t *__restrict__ planes, int64_t snp, int64_t snp_pad,
-                                    const int32_t *__restrict__ perm, int64_t npos, int A, int a_pad, int s_pad,
-                                    uint8_t *__restrict__ out) {
+                                    const int32_t *__restrict__ perm, const FoldLayout *__restrict__ flp, int64_t npos,
+                                    int A, int a_pad, int s_pad, uint8_t *__restrict__ out) {
+    const FoldLayout &fl = *flp;
     const int64_t pos = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= npos) return;
     const int32_t col = perm[pos];
     if (col < 0) return;
-    const int b = (int) (pos / (32 * BW)), w = (int) ((pos / 32) % BW), bit = (int) (pos & 31);
-    int wp = w;
-    if (BW == 8) wp = (((w >> 2) ^ swizzle_of(snp)) << 2) | (w & 3);
+    const int b = (int) (pos / (32 * fl.bw)), w = (int) ((pos / 32) % fl.bw), bit = (int) (pos & 31);
     const int dst = col < A ? col : a_pad + (col - A);
     for (int g = 0; g < 3; g++) {
-        uint32_t word = planes[(((int64_t) b * snp_pad + snp) * 3 + g) * BW + wp];
+        const uint32_t word = planes[plane_word(fl, snp_pad, b, snp, g, w)];
         out[(int64_t) g * s_pad + dst] = ((word >> bit) & 1u) ? 0xFF : 0x00;
     }
 }
@@ -76,15 +74,9 @@ __global__ void unpack_masks_kernel(const uint32_t *__restrict__ planes, int64_t
 // ============================================================================
 // Shared pieces of the search kernels
 // ============================================================================
-constexpr int kStages = 4;
-constexpr int kConsumerWarps = 8;
-constexpr int kConsumers = kConsumerWarps * 32;
-constexpr int kSearchThreads = kConsumers + 32;   // + producer warp
-
 struct __align__(16) SearchCtl {
-    uint64_t full[kStages];
-    uint64_t empty[kStages];
-    int4 meta[kStages];            // x = block index (-1: no more work), y/z/w = tile origins
+    uint64_t full[2];              // one mbarrier per stage
+    int4 meta[3];                  // step descriptors: x = chunk (-1: no more work), y/z/w = tile origins
     long long thr[kMaxFolds];      // score a candidate must reach to be offered to the list
     int lock[kMaxFolds];
     int cnt[kMaxFolds];
@@ -92,16 +84,34 @@ struct __align__(16) SearchCtl {
     FoldLayout fl;
 };
 
-// ---- top-N list maintenance (one list per CTA and fold, in global memory) ----
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// dynamic shared memory map of the search kernels (the host uses the same function to size the launch)
+struct SmemMap {
+    size_t stage0, stage_bytes, counters, desc, lists, total;
+};
+__host__ __device__ inline SmemMap search_smem_map(const FoldLayout &fl, int rows, int ncells, int nthreads, int rank, bool lists_in_smem) {
+    SmemMap m;
+    m.stage0 = align_up(sizeof(SearchCtl), 128);
+    m.stage_bytes = align_up((size_t) rows * fl.row_words * 4, 128);
+    m.counters = m.stage0 + 2 * m.stage_bytes;
+    const int nwc = fl.single ? fl.nblocks / 4 : fl.F;
+    m.desc = m.counters + (size_t) ncells * nwc * nthreads * 4;
+    m.lists = align_up(m.desc + (fl.single ? 0 : (size_t) fl.nblocks * 2), 16);
+    m.total = m.lists + (lists_in_smem ? (size_t) fl.F * rank * sizeof(Cand) : 0);
+    return m;
+}
+
+// ---- top-N list maintenance (one list per CTA and fold) ------------------------
 // Called by a full warp with a warp-uniform candidate.  Replaces
 // add_to_model_ranking (model.c:481-521) with a deterministic order.
-__device__ __forceinline__ void warp_offer(SearchCtl *ctl, const SearchArgs &a, int f, const Cand &c, int lane) {
+__device__ __forceinline__ void warp_offer(SearchCtl *ctl, const SearchArgs &a, Cand *lists, int f, const Cand &c, int lane) {
     if (lane == 0) {
-        while (atomicCAS(&ctl->lock[f], 0, 1) != 0) __nanosleep(32);
+        while (atomicCAS(&ctl->lock[f], 0, 1) != 0) __nanosleep(20);
     }
     __syncwarp();
     __threadfence_block();
-    Cand *list = a.lists + ((size_t) blockIdx.x * ctl->fl.F + f) * a.rank;
+    Cand *list = lists + (size_t) f * a.rank;
     // every lane reads the list state BEFORE lane 0 modifies it, so the decisions below are warp-uniform
     const int cnt = *reinterpret_cast<volatile int *>(&ctl->cnt[f]);
     bool replace = false;
@@ -164,13 +174,36 @@ __device__ __forceinline__ void warp_offer(SearchCtl *ctl, const SearchArgs &a, 
     __syncwarp();
 }
 
-// ---- per-combination epilogue -------------------------------------------------
-// cnts: this thread's private counters, word (c, k) at cnts[(c * nwc + k) * kConsumers].
-// CBITS == 8 : word k of cell c = counts of segments 4k..4k+3 = (A_2k, U_2k, A_2k+1, U_2k+1)
-// CBITS == 16: word k of cell c = counts of segments 2k, 2k+1  = (A_k, U_k)
-template <int NCELLS, int CBITS>
-__device__ __forceinline__ void combo_epilogue(SearchCtl *ctl, const SearchArgs &a, const uint32_t *cnts, int nwc,
-                                               bool valid, int si, int sj, int sk, int lane) {
+// offer the tuples of the lanes whose score reaches the fold's running threshold
+__device__ __forceinline__ void offer_fold(SearchCtl *ctl, const SearchArgs &a, Cand *lists, int f, bool valid, long long score,
+                                           bool degenerate, int npos, int nneg, int si, int sj, int sk, uint32_t mask, int tp, int fp,
+                                           int lane) {
+    const long long thr = *reinterpret_cast<volatile long long *>(&ctl->thr[f]);
+    unsigned want = __ballot_sync(0xffffffffu, valid && score >= thr);
+    while (want) {
+        const int src = __ffs(want) - 1;
+        want &= want - 1;
+        Cand c;
+        c.i = __shfl_sync(0xffffffffu, si, src);
+        c.j = __shfl_sync(0xffffffffu, sj, src);
+        c.k = __shfl_sync(0xffffffffu, sk, src);
+        c.mask = __shfl_sync(0xffffffffu, mask, src);
+        c.tp = __shfl_sync(0xffffffffu, tp, src);
+        c.fp = __shfl_sync(0xffffffffu, fp, src);
+        c.ba = degenerate ? -INFINITY : balanced_accuracy(c.tp, c.fp, npos, nneg);
+        warp_offer(ctl, a, lists, f, c, lane);
+    }
+}
+
+// ---- per-tuple epilogue ---------------------------------------------------------
+// cnts: this thread's private counters, word (c, k) at cnts[(c * nwc + k) * nthreads].
+// U8  (single-block segments): word k of cell c = bytes (A_2k, A_2k+1, U_2k, U_2k+1) of folds 2k and 2k+1
+// !U8 (multi-block segments) : word f of cell c = A_f | U_f << 16
+//
+// General version: any class sizes, the exact high-risk rule with its float32 replay.
+template <int NCELLS, bool U8>
+__device__ __forceinline__ void epilogue_general(SearchCtl *ctl, const SearchArgs &a, Cand *lists, const uint32_t *cnts, int nwc,
+                                                 int nthreads, bool valid, int si, int sj, int sk, int lane) {
     const FoldLayout &fl = ctl->fl;
     const RiskParams rp = risk_params(fl);
     const int nfolds = fl.F;
@@ -180,10 +213,10 @@ __device__ __forceinline__ void combo_epilogue(SearchCtl *ctl, const SearchArgs 
     for (int k = 0; k < nwc; k++) {
 #pragma unroll
         for (int c = 0; c < NCELLS; c++) {
-            uint32_t w = cnts[(c * nwc + k) * kConsumers];
-            if constexpr (CBITS == 8) {
-                totA[c] = __dp4a(w, 0x00010001u, (uint32_t) totA[c]);
-                totU[c] = __dp4a(w, 0x01000100u, (uint32_t) totU[c]);
+            const uint32_t w = cnts[(c * nwc + k) * nthreads];
+            if constexpr (U8) {
+                totA[c] = __dp4a(w, 0x00000101u, (uint32_t) totA[c]);
+                totU[c] = __dp4a(w, 0x01010000u, (uint32_t) totU[c]);
             } else {
                 totA[c] += (int) (w & 0xffffu);
                 totU[c] += (int) (w >> 16);
@@ -193,13 +226,12 @@ __device__ __forceinline__ void combo_epilogue(SearchCtl *ctl, const SearchArgs 
     for (int f = 0; f < nfolds; f++) {
         int tp = 0, fp = 0;
         uint32_t mask = 0;
-        const int k = (CBITS == 8) ? (f >> 1) : f;
-        const int sh = (CBITS == 8) ? ((f & 1) * 16) : 0;
+        const int k = U8 ? (f >> 1) : f;
 #pragma unroll
         for (int c = 0; c < NCELLS; c++) {
-            uint32_t w = cnts[(c * nwc + k) * kConsumers] >> sh;
+            const uint32_t w = cnts[(c * nwc + k) * nthreads];
             int inA, inU;
-            if constexpr (CBITS == 8) { inA = (int) (w & 0xffu); inU = (int) ((w >> 8) & 0xffu); }
+            if constexpr (U8) { inA = (int) ((w >> ((f & 1) * 8)) & 0xffu); inU = (int) ((w >> (16 + (f & 1) * 8)) & 0xffu); }
             else { inA = (int) (w & 0xffffu); inU = (int) (w >> 16); }
             const int trA = totA[c] - inA, trU = totU[c] - inU;
             const bool r = high_risk(trA, trU, rp);          // always on the TRAINING table (epistasis.c:34)
@@ -212,326 +244,454 @@ __device__ __forceinline__ void combo_epilogue(SearchCtl *ctl, const SearchArgs 
         const int nneg = a.training ? fl.U - fl.u_in[f] : fl.u_in[f];
         const bool degenerate = (npos == 0 || nneg == 0);   // BA = 0/0 = NaN in the reference (model.c:473)
         const long long score = degenerate ? LLONG_MIN : ba_score(tp, fp, npos, nneg);
-        const long long thr = *reinterpret_cast<volatile long long *>(&ctl->thr[f]);
-        unsigned want = __ballot_sync(0xffffffffu, valid && score >= thr);
-        while (want) {
-            const int src = __ffs(want) - 1;
-            want &= want - 1;
-            Cand c;
-            c.i = __shfl_sync(0xffffffffu, si, src);
-            c.j = __shfl_sync(0xffffffffu, sj, src);
-            c.k = __shfl_sync(0xffffffffu, sk, src);
-            c.mask = __shfl_sync(0xffffffffu, mask, src);
-            c.tp = __shfl_sync(0xffffffffu, tp, src);
-            c.fp = __shfl_sync(0xffffffffu, fp, src);
-            c.ba = degenerate ? -INFINITY : balanced_accuracy(c.tp, c.fp, npos, nneg);
-            warp_offer(ctl, a, f, c, lane);
+        offer_fold(ctl, a, lists, f, valid, score, degenerate, npos, nneg, si, sj, sk, mask, tp, fp, lane);
+    }
+}
+
+// d = c + a.u16[0] * b.s8[0] + a.u16[1] * b.s8[1]
+__device__ __forceinline__ int dp2a_lo_us(uint32_t a16x2, uint32_t b8, int c) {
+    int d;
+    asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a16x2), "r"(b8), "r"(c));
+    return d;
+}
+
+// one fold of the balanced epilogue; in_of(c) returns the in-fold pair (cases | controls << 16) of cell c
+template <int NCELLS, typename InOf>
+__device__ __forceinline__ void balanced_fold(SearchCtl *ctl, const SearchArgs &a, Cand *lists, const uint32_t (&tot)[NCELLS], int f,
+                                              InOf in_of, bool valid, int si, int sj, int sk, int lane) {
+    const FoldLayout &fl = ctl->fl;
+    uint32_t tpfp = 0, mask = 0;
+#pragma unroll
+    for (int c = 0; c < NCELLS; c++) {
+        const uint32_t in = in_of(c);
+        const uint32_t tr = tot[c] - in;                     // no borrow: every half of tot >= the half of in
+        const int d = dp2a_lo_us(tr, 0x0000FF01u, 0);        // trA - trU
+        const bool r = (d >= 0) && (tr != 0);                // d >= 0 and trA == 0 imply trU == 0
+        const uint32_t ev = a.training ? tr : in;
+        tpfp += r ? ev : 0u;
+        mask |= (r ? 1u : 0u) << c;
+    }
+    const int tp = (int) (tpfp & 0xffffu), fp = (int) (tpfp >> 16);
+    const int npos = a.training ? fl.A - fl.a_in[f] : fl.a_in[f];
+    const int nneg = a.training ? fl.U - fl.u_in[f] : fl.u_in[f];
+    const bool degenerate = (npos == 0 || nneg == 0);
+    const long long score = degenerate ? LLONG_MIN : ba_score(tp, fp, npos, nneg);
+    offer_fold(ctl, a, lists, f, valid, score, degenerate, npos, nneg, si, sj, sk, mask, tp, fp, lane);
+}
+
+// Fast version for balanced data sets (A == U <= 65535): every count pair travels as
+// one register (cases | controls << 16); r = A/U = 1 makes the float32 rule exact,
+// risky <=> trA >= trU and trA > 0 (see high_risk()).
+template <int NCELLS, bool U8>
+__device__ __forceinline__ void epilogue_balanced(SearchCtl *ctl, const SearchArgs &a, Cand *lists, const uint32_t *cnts, int nwc,
+                                                  int nthreads, bool valid, int si, int sj, int sk, int lane) {
+    const int nfolds = ctl->fl.F;
+    uint32_t tot[NCELLS];                     // total cases | total controls << 16
+    if constexpr (U8) {
+        uint32_t tA[NCELLS], tU[NCELLS];
+#pragma unroll
+        for (int c = 0; c < NCELLS; c++) { tA[c] = 0; tU[c] = 0; }
+        for (int k = 0; k < nwc; k++) {
+#pragma unroll
+            for (int c = 0; c < NCELLS; c++) {
+                const uint32_t w = cnts[(c * nwc + k) * nthreads];
+                tA[c] = __dp4a(w, 0x00000101u, tA[c]);
+                tU[c] = __dp4a(w, 0x01010000u, tU[c]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < NCELLS; c++) tot[c] = tA[c] | (tU[c] << 16);
+        for (int k = 0; 2 * k < nfolds; k++) {
+            uint32_t w[NCELLS];
+#pragma unroll
+            for (int c = 0; c < NCELLS; c++) w[c] = cnts[(c * nwc + k) * nthreads];
+            balanced_fold<NCELLS>(ctl, a, lists, tot, 2 * k, [&](int c) { return __byte_perm(w[c], 0u, 0x4240); }, valid, si, sj, sk, lane);
+            if (2 * k + 1 < nfolds)
+                balanced_fold<NCELLS>(ctl, a, lists, tot, 2 * k + 1, [&](int c) { return __byte_perm(w[c], 0u, 0x4341); }, valid, si, sj, sk, lane);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < NCELLS; c++) tot[c] = 0;
+        for (int k = 0; k < nwc; k++) {
+#pragma unroll
+            for (int c = 0; c < NCELLS; c++) tot[c] += cnts[(c * nwc + k) * nthreads];
+        }
+        for (int f = 0; f < nfolds; f++)
+            balanced_fold<NCELLS>(ctl, a, lists, tot, f, [&](int c) { return cnts[(c * nwc + f) * nthreads]; }, valid, si, sj, sk, lane);
+    }
+}
+
+// shift of the byte counter of block q (0..3) of a four-block group: segments (2k A, 2k U, 2k+1 A, 2k+1 U)
+// land in bytes (0, 2, 1, 3), i.e. the word reads (A_2k, A_2k+1, U_2k, U_2k+1)
+__host__ __device__ constexpr uint32_t group_shift(int q) { return q == 0 ? 0u : (q == 1 ? 16u : (q == 2 ? 8u : 24u)); }
+
+// block Q (0..3) of a four-block group, single-block segments: the nine (27) cell counts go to byte group_shift(Q) of pk[]
+template <int BW, int Q>
+__device__ __forceinline__ void single_block2(const uint32_t *irow, const uint32_t *jrow, uint32_t (&pk)[9]) {
+    constexpr int off = Q * 3 * BW;
+    uint32_t pj[3][BW];
+#pragma unroll
+    for (int g = 0; g < 3; g++) load_plane<BW>(jrow + off + g * BW, pj[g]);
+#pragma unroll
+    for (int ga = 0; ga < 3; ga++) {
+        uint32_t pi[BW];
+        load_plane<BW>(irow + off + ga * BW, pi);
+#pragma unroll
+        for (int gb = 0; gb < 3; gb++) pk[ga * 3 + gb] = cell_count2_acc<BW, (1u << group_shift(Q))>(pi, pj[gb], pk[ga * 3 + gb]);
+    }
+}
+template <int BW, int Q>
+__device__ __forceinline__ void single_block3(const uint32_t *irow, const uint32_t *jrow, const uint32_t *krow, uint32_t (&pk)[27]) {
+    constexpr int off = Q * 3 * BW;
+    uint32_t pl[3][BW];
+#pragma unroll
+    for (int g = 0; g < 3; g++) load_plane<BW>(krow + off + g * BW, pl[g]);
+#pragma unroll
+    for (int ga = 0; ga < 3; ga++) {
+        uint32_t pi[BW];
+        load_plane<BW>(irow + off + ga * BW, pi);
+#pragma unroll
+        for (int gb = 0; gb < 3; gb++) {
+            uint32_t pj[BW];
+            load_plane<BW>(jrow + off + gb * BW, pj);
+#pragma unroll
+            for (int gc = 0; gc < 3; gc++) {
+                const int c = ga * 9 + gb * 3 + gc;
+                pk[c] = cell_count3_acc<BW, (1u << group_shift(Q))>(pi, pj, pl[gc], pk[c]);
+            }
         }
     }
 }
 
-template <int CBITS>
-__device__ __forceinline__ void store_count(uint32_t *cnts, int c, int nwc, int seg, uint32_t v) {
-    if constexpr (CBITS == 8) {
-        reinterpret_cast<uint8_t *>(cnts + (c * nwc + (seg >> 2)) * kConsumers)[seg & 3] = (uint8_t) v;
-    } else {
-        reinterpret_cast<uint16_t *>(cnts + (c * nwc + (seg >> 1)) * kConsumers)[seg & 1] = (uint16_t) v;
-    }
-}
-
-__host__ __device__ inline int words_per_cell(int nseg, int cbits) { return cbits == 8 ? (nseg + 3) / 4 : (nseg + 1) / 2; }
-
-// dynamic shared memory: [SearchCtl][stage ring][counters]
-template <int BW>
-__host__ __device__ inline size_t stage_words(int rows) { return (size_t) rows * 3 * BW; }
-
-// ============================================================================
-// Order 2
-// ============================================================================
-// unit = (i-tile of TI = 8*PPT rows, j-tile of 32 rows); warp w, slot p <-> i = i0 + w*PPT + p; lane <-> j = j0 + lane
-template <int BW, int CBITS, int PPT, bool SINGLE>
-__global__ void __launch_bounds__(kSearchThreads) search2_kernel(const SearchArgs a) {
-    constexpr int TI = kConsumerWarps * PPT;
-    constexpr int ROWW = 3 * BW;                      // words per staged row
-    constexpr int STAGEW = (TI + kTileJ) * ROWW;
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    SearchCtl *ctl = reinterpret_cast<SearchCtl *>(smem_raw);
-    uint32_t *stage = reinterpret_cast<uint32_t *>(smem_raw + ((sizeof(SearchCtl) + 127) / 128) * 128);
-    uint32_t *cnt_base = stage + kStages * STAGEW;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nseg = a.fl->nseg, nblocks = a.fl->nblocks;
-    const int nwc = words_per_cell(nseg, CBITS);
-
+// common prologue: barriers, control block, counters, block descriptors
+template <bool SINGLE>
+__device__ __forceinline__ void search_init(SearchCtl *ctl, const SearchArgs &a, uint32_t *cnt_base, size_t cnt_words, uint16_t *desc) {
+    const int tid = threadIdx.x;
     if (tid == 0) {
-        for (int s = 0; s < kStages; s++) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], kConsumerWarps); }
+        mbar_init(&ctl->full[0], 1);
+        mbar_init(&ctl->full[1], 1);
         mbar_fence_init();
         ctl->fl = *a.fl;
     }
     if (tid < kMaxFolds) { ctl->thr[tid] = LLONG_MIN; ctl->lock[tid] = 0; ctl->cnt[tid] = 0; ctl->min_idx[tid] = 0; }
-    for (int x = tid; x < PPT * 9 * nwc * kConsumers; x += kSearchThreads) cnt_base[x] = 0;   // padding bytes must read 0
+    for (size_t x = tid; x < cnt_words; x += blockDim.x) cnt_base[x] = 0;   // halves that are never written must read 0
+    if constexpr (!SINGLE) {
+        const int nb = a.fl->nblocks;
+        for (int x = tid; x < nb; x += blockDim.x) desc[x] = a.blk_desc[x];
+    }
     __syncthreads();
+}
 
-    if (warp == kConsumerWarps) {
-        // ------------------------------ producer ------------------------------
-        if (lane == 0) {
-            uint32_t it = 0;
-            const char *planes = reinterpret_cast<const char *>(a.planes);
-            for (;;) {
-                const unsigned long long u = atomicAdd(a.unit_counter, 1ULL);
-                if (u >= (unsigned long long) a.num_units) break;
-                int lo = 0, hi = a.n_it - 1;
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if ((unsigned long long) a.unit_prefix[mid] <= u) lo = mid; else hi = mid - 1;
-                }
-                const int i0 = (a.it0 + lo) * TI;
-                const int j0 = (a.unit_jt0[lo] + (int) (u - (unsigned long long) a.unit_prefix[lo])) * kTileJ;
-                for (int b = 0; b < nblocks; b++, it++) {
-                    const int st = it % kStages;
-                    mbar_wait(&ctl->empty[st], ((it / kStages) & 1) ^ 1);
-                    ctl->meta[st] = make_int4(b, i0, j0, 0);
-                    mbar_arrive_expect_tx(&ctl->full[st], STAGEW * 4);
-                    const char *src = planes + (int64_t) b * a.snp_pad * (ROWW * 4);
-                    uint32_t *dst = stage + st * STAGEW;
-                    bulk_g2s(dst, src + (int64_t) i0 * (ROWW * 4), TI * ROWW * 4, &ctl->full[st]);
-                    bulk_g2s(dst + TI * ROWW, src + (int64_t) j0 * (ROWW * 4), kTileJ * ROWW * 4, &ctl->full[st]);
-                }
-            }
-            const int st = it % kStages;
-            mbar_wait(&ctl->empty[st], ((it / kStages) & 1) ^ 1);
-            ctl->meta[st] = make_int4(-1, 0, 0, 0);
-            mbar_arrive(&ctl->full[st]);
+// common tail of the kernel: publish the CTA's lists
+__device__ __forceinline__ void search_publish(SearchCtl *ctl, const SearchArgs &a, Cand *lists) {
+    __syncthreads();
+    const int F = ctl->fl.F;
+    if (a.lists_in_smem) {
+        Cand *dst = a.lists + (size_t) blockIdx.x * F * a.rank;
+        const int4 *s = reinterpret_cast<const int4 *>(lists);
+        int4 *d = reinterpret_cast<int4 *>(dst);
+        for (int x = threadIdx.x; x < F * a.rank * 2; x += blockDim.x) d[x] = s[x];
+    }
+    if (threadIdx.x < F) a.list_cnt[(size_t) blockIdx.x * F + threadIdx.x] = ctl->cnt[threadIdx.x];
+}
+
+// ============================================================================
+// Order 2
+// ============================================================================
+// unit = (i-tile of TI = nwarps rows, j-tile of 32 rows); warp w <-> i = i0 + w; lane <-> j = j0 + lane
+template <int BW, bool SINGLE, bool BALANCED>
+__global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const SearchArgs a) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    SearchCtl *ctl = reinterpret_cast<SearchCtl *>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nthreads = blockDim.x, TI = nthreads >> 5;
+    const SmemMap sm = search_smem_map(*a.fl, TI + kTileJ, 9, nthreads, a.rank, a.lists_in_smem != 0);
+    uint32_t *cnt_base = reinterpret_cast<uint32_t *>(smem_raw + sm.counters);
+    uint16_t *desc = reinterpret_cast<uint16_t *>(smem_raw + sm.desc);
+    Cand *lists = a.lists_in_smem ? reinterpret_cast<Cand *>(smem_raw + sm.lists) : a.lists + (size_t) blockIdx.x * a.fl->F * a.rank;
+    search_init<SINGLE>(ctl, a, cnt_base, (sm.desc - sm.counters) / 4, desc);
+
+    const int nblocks = ctl->fl.nblocks, cb = ctl->fl.cb, nchunks = ctl->fl.nchunks, roww = ctl->fl.row_words;
+    const int nwc = SINGLE ? nblocks / 4 : ctl->fl.F;
+    const uint32_t row_bytes = (uint32_t) roww * 4;
+
+    // ---- step sequencing (thread 0): units blockIdx.x, blockIdx.x + gridDim.x, ... each cut into nchunks steps ----
+    long long u = blockIdx.x;
+    int grp = 0, chunk = 0, cur_i0 = 0, cur_j0 = 0;
+    auto decode = [&]() {
+        while (grp + 1 < a.n_it && a.unit_prefix[grp + 1] <= u) grp++;
+        cur_i0 = (a.it0 + grp) * TI;
+        cur_j0 = (a.unit_jt0[grp] + (int) (u - a.unit_prefix[grp])) * kTileJ;
+    };
+    auto issue = [&](int st, int ch, int i0, int j0) {
+        uint8_t *dst = smem_raw + sm.stage0 + (size_t) st * sm.stage_bytes;
+        const char *src = reinterpret_cast<const char *>(a.planes) + (int64_t) ch * a.snp_pad * row_bytes;
+        mbar_arrive_expect_tx(&ctl->full[st], (uint32_t) (TI + kTileJ) * row_bytes);
+        bulk_g2s(dst, src + (int64_t) i0 * row_bytes, (uint32_t) TI * row_bytes, &ctl->full[st]);
+        bulk_g2s(dst + (size_t) TI * row_bytes, src + (int64_t) j0 * row_bytes, (uint32_t) kTileJ * row_bytes, &ctl->full[st]);
+    };
+    if (tid == 0) {
+        if (u < a.num_units) {
+            decode();
+            ctl->meta[0] = make_int4(0, cur_i0, cur_j0, 0);
+            issue(0, 0, cur_i0, cur_j0);
+        } else {
+            ctl->meta[0] = make_int4(-1, 0, 0, 0);
         }
-    } else {
-        // ------------------------------ consumers ------------------------------
-        uint32_t *cnts = cnt_base + tid;          // + (p*9 + c) * nwc * kConsumers + k * kConsumers
-        uint32_t acc[PPT][9];
-#pragma unroll
-        for (int p = 0; p < PPT; p++)
-#pragma unroll
-            for (int c = 0; c < 9; c++) acc[p][c] = 0;
+    }
 
-        for (uint32_t it = 0;; it++) {
-            const int st = it % kStages;
-            mbar_wait(&ctl->full[st], (it / kStages) & 1);
-            const int4 meta = ctl->meta[st];
-            if (meta.x < 0) break;
-            const int b = meta.x, i0 = meta.y, j0 = meta.z;
-            const uint32_t *sbase = stage + st * STAGEW;
-            const unsigned desc = a.blk_desc[b];
-            const int seg = desc & 0x7fff;
-
-            uint32_t pj[3][BW];
-            {
-                const uint32_t *jrow = sbase + (TI + lane) * ROWW;
-                const int swz = swizzle_of(j0 + lane);
+    uint32_t *cnts = cnt_base + tid;          // + (c * nwc + k) * nthreads
+    uint32_t acc[9];
 #pragma unroll
-                for (int g = 0; g < 3; g++) load_plane<BW>(jrow, g, swz, pj[g]);
+    for (int c = 0; c < 9; c++) acc[c] = 0;
+
+    for (uint32_t s = 0;; s++) {
+        const int st = s & 1;
+        int4 next = make_int4(-1, 0, 0, 0);
+        if (tid == 0) {
+            if (u < a.num_units) {
+                // the step after this one
+                if (++chunk == nchunks) {
+                    chunk = 0;
+                    u += gridDim.x;
+                    if (u < a.num_units) decode();
+                }
+                if (u < a.num_units) next = make_int4(chunk, cur_i0, cur_j0, 0);
             }
+            ctl->meta[(s + 1) % 3] = next;
+        }
+        __syncthreads();                       // everyone is done with step s-1: its stage may be overwritten
+        if (tid == 0 && next.x >= 0) issue(st ^ 1, next.x, next.y, next.z);
+        const int4 meta = ctl->meta[s % 3];
+        if (meta.x < 0) break;
+        const int ch = meta.x, i0 = meta.y, j0 = meta.z;
+        if (ch == 0 && warp == 0 && lane < ctl->fl.F) atomicMax(&ctl->thr[lane], __ldcg(a.gthr + lane));
+        mbar_wait(&ctl->full[st], (s >> 1) & 1);
+
+        const uint32_t *sbase = reinterpret_cast<const uint32_t *>(smem_raw + sm.stage0 + (size_t) st * sm.stage_bytes);
+        const uint32_t *irow = sbase + (size_t) warp * roww;
+        const uint32_t *jrow = sbase + (size_t) (TI + lane) * roww;
+        const int b_lo = ch * cb, b_hi = min(nblocks, b_lo + cb);
+
+        if constexpr (SINGLE) {
+            for (int b4 = b_lo; b4 < b_hi; b4 += 4) {
+                uint32_t pk[9];
 #pragma unroll
-            for (int p = 0; p < PPT; p++) {
-                const int il = warp * PPT + p;
-                const uint32_t *irow = sbase + il * ROWW;
-                const int swz = swizzle_of(i0 + il);
+                for (int c = 0; c < 9; c++) pk[c] = 0;
+                const int off = (b4 - b_lo) * 3 * BW;
+                single_block2<BW, 0>(irow + off, jrow + off, pk);
+                single_block2<BW, 1>(irow + off, jrow + off, pk);
+                single_block2<BW, 2>(irow + off, jrow + off, pk);
+                single_block2<BW, 3>(irow + off, jrow + off, pk);
+                const int k = b4 >> 2;
+#pragma unroll
+                for (int c = 0; c < 9; c++) cnts[(c * nwc + k) * nthreads] = pk[c];
+            }
+        } else {
+            for (int b = b_lo; b < b_hi; b++) {
+                const int off = (b - b_lo) * 3 * BW;
+                uint32_t pj[3][BW];
+#pragma unroll
+                for (int g = 0; g < 3; g++) load_plane<BW>(jrow + off + g * BW, pj[g]);
 #pragma unroll
                 for (int ga = 0; ga < 3; ga++) {
                     uint32_t pi[BW];
-                    load_plane<BW>(irow, ga, swz, pi);
+                    load_plane<BW>(irow + off + ga * BW, pi);
 #pragma unroll
-                    for (int gb = 0; gb < 3; gb++) {
-                        const uint32_t n = cell_count2<BW>(pi, pj[gb]);
-                        if constexpr (SINGLE) store_count<CBITS>(cnts + (p * 9) * nwc * kConsumers, ga * 3 + gb, nwc, seg, n);
-                        else acc[p][ga * 3 + gb] += n;
-                    }
+                    for (int gb = 0; gb < 3; gb++) acc[ga * 3 + gb] = cell_count2_acc<BW, 1u>(pi, pj[gb], acc[ga * 3 + gb]);
                 }
-            }
-            if constexpr (!SINGLE) {
-                if (desc & 0x8000u) {
+                const unsigned d = desc[b];
+                if (d & 0x8000u) {
+                    const int seg = d & 0x7fff;
 #pragma unroll
-                    for (int p = 0; p < PPT; p++)
-#pragma unroll
-                        for (int c = 0; c < 9; c++) {
-                            store_count<CBITS>(cnts + (p * 9) * nwc * kConsumers, c, nwc, seg, acc[p][c]);
-                            acc[p][c] = 0;
-                        }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ctl->empty[st]);
-
-            if (b == 0 && warp == 0 && lane < ctl->fl.F) atomicMax(&ctl->thr[lane], __ldcg(a.gthr + lane));
-
-            if (b == nblocks - 1) {
-                const int j = j0 + lane;
-#pragma unroll 1
-                for (int p = 0; p < PPT; p++) {
-                    const int i = i0 + warp * PPT + p;
-                    bool valid = (i < j) && (j < a.nv);
-                    if (valid) {
-                        const uint64_t idx = pair_index((uint64_t) a.nv, (uint64_t) i, (uint64_t) j);
-                        valid = idx >= a.first && idx < a.last;
+                    for (int c = 0; c < 9; c++) {
+                        reinterpret_cast<uint16_t *>(cnts + (c * nwc + (seg >> 1)) * nthreads)[seg & 1] = (uint16_t) acc[c];
+                        acc[c] = 0;
                     }
-                    combo_epilogue<9, CBITS>(ctl, a, cnts + (p * 9) * nwc * kConsumers, nwc, valid, i, j, -1, lane);
                 }
             }
         }
-        // all consumer warps are done inserting: publish list sizes
-        asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));
-        if (tid < ctl->fl.F) a.list_cnt[(size_t) blockIdx.x * ctl->fl.F + tid] = ctl->cnt[tid];
+
+        if (ch == nchunks - 1) {
+            const int i = i0 + warp, j = j0 + lane;
+            bool valid = (i < j) && (j < a.nv);
+            if (valid) {
+                const uint64_t idx = pair_index((uint64_t) a.nv, (uint64_t) i, (uint64_t) j);
+                valid = idx >= a.first && idx < a.last;
+            }
+            if (__any_sync(0xffffffffu, valid)) {
+                if constexpr (BALANCED) epilogue_balanced<9, SINGLE>(ctl, a, lists, cnts, nwc, nthreads, valid, i, j, -1, lane);
+                else epilogue_general<9, SINGLE>(ctl, a, lists, cnts, nwc, nthreads, valid, i, j, -1, lane);
+            }
+        }
     }
+    search_publish(ctl, a, lists);
 }
 
 // ============================================================================
 // Order 3
 // ============================================================================
-// unit = (i, j-tile of 8 rows, k-tile of 32 rows); warp w <-> j = j0 + w; lane <-> k = k0 + lane; one triple per thread.
-// Work list: producer takes (i, j-tile) super-units from the global counter and walks the k-tiles itself.
-template <int BW, int CBITS, bool SINGLE>
-__global__ void __launch_bounds__(kSearchThreads) search3_kernel(const SearchArgs a) {
-    constexpr int TJ = kConsumerWarps;                // 8 j rows
-    constexpr int ROWW = 3 * BW;
-    constexpr int ROWS = 1 + TJ + kTileJ;             // i row, j rows, k rows
-    constexpr int STAGEW = ((ROWS * ROWW + 3) / 4) * 4;
+// unit = (i, j-tile of TJ = nwarps rows); the CTA walks the k-tiles of the unit itself.
+// warp w <-> j = j0 + w; lane <-> k = k0 + lane; one triple per thread and (unit, k-tile).
+template <int BW, bool SINGLE, bool BALANCED>
+__global__ void __launch_bounds__(kMaxWarps * 32, 1) search3_kernel(const SearchArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     SearchCtl *ctl = reinterpret_cast<SearchCtl *>(smem_raw);
-    uint32_t *stage = reinterpret_cast<uint32_t *>(smem_raw + ((sizeof(SearchCtl) + 127) / 128) * 128);
-    uint32_t *cnt_base = stage + kStages * STAGEW;
-
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nseg = a.fl->nseg, nblocks = a.fl->nblocks;
-    const int nwc = words_per_cell(nseg, CBITS);
+    const int nthreads = blockDim.x, TJ = nthreads >> 5;
+    const SmemMap sm = search_smem_map(*a.fl, 1 + TJ + kTileJ, 27, nthreads, a.rank, a.lists_in_smem != 0);
+    uint32_t *cnt_base = reinterpret_cast<uint32_t *>(smem_raw + sm.counters);
+    uint16_t *desc = reinterpret_cast<uint16_t *>(smem_raw + sm.desc);
+    Cand *lists = a.lists_in_smem ? reinterpret_cast<Cand *>(smem_raw + sm.lists) : a.lists + (size_t) blockIdx.x * a.fl->F * a.rank;
+    search_init<SINGLE>(ctl, a, cnt_base, (sm.desc - sm.counters) / 4, desc);
 
+    const int nblocks = ctl->fl.nblocks, cb = ctl->fl.cb, nchunks = ctl->fl.nchunks, roww = ctl->fl.row_words;
+    const int nwc = SINGLE ? nblocks / 4 : ctl->fl.F;
+    const uint32_t row_bytes = (uint32_t) roww * 4;
+    const int nkt = (a.nv + kTileJ - 1) / kTileJ;
+
+    // ---- step sequencing (thread 0): unit -> k-tiles -> chunks ----
+    long long u = blockIdx.x;
+    int grp = 0, chunk = 0, cur_i = 0, cur_j0 = 0, cur_kt = 0;
+    auto decode = [&]() {
+        while (grp + 1 < a.n_it && a.unit_prefix[grp + 1] <= u) grp++;
+        cur_i = a.it0 + grp;
+        cur_j0 = (a.unit_jt0[grp] + (int) (u - a.unit_prefix[grp])) * TJ;
+        cur_kt = (cur_j0 + 1) / kTileJ;        // first k-tile that can hold k > j0
+    };
+    auto issue = [&](int st, int ch, int i, int j0, int k0) {
+        uint8_t *dst = smem_raw + sm.stage0 + (size_t) st * sm.stage_bytes;
+        const char *src = reinterpret_cast<const char *>(a.planes) + (int64_t) ch * a.snp_pad * row_bytes;
+        mbar_arrive_expect_tx(&ctl->full[st], (uint32_t) (1 + TJ + kTileJ) * row_bytes);
+        bulk_g2s(dst, src + (int64_t) i * row_bytes, row_bytes, &ctl->full[st]);
+        bulk_g2s(dst + row_bytes, src + (int64_t) j0 * row_bytes, (uint32_t) TJ * row_bytes, &ctl->full[st]);
+        bulk_g2s(dst + (size_t) (1 + TJ) * row_bytes, src + (int64_t) k0 * row_bytes, (uint32_t) kTileJ * row_bytes, &ctl->full[st]);
+    };
+    // meta: x = chunk, y = i, z = j0, w = k0
     if (tid == 0) {
-        for (int s = 0; s < kStages; s++) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], kConsumerWarps); }
-        mbar_fence_init();
-        ctl->fl = *a.fl;
+        if (u < a.num_units) {
+            decode();
+            ctl->meta[0] = make_int4(0, cur_i, cur_j0, cur_kt * kTileJ);
+            issue(0, 0, cur_i, cur_j0, cur_kt * kTileJ);
+        } else {
+            ctl->meta[0] = make_int4(-1, 0, 0, 0);
+        }
     }
-    if (tid < kMaxFolds) { ctl->thr[tid] = LLONG_MIN; ctl->lock[tid] = 0; ctl->cnt[tid] = 0; ctl->min_idx[tid] = 0; }
-    for (int x = tid; x < 27 * nwc * kConsumers; x += kSearchThreads) cnt_base[x] = 0;
-    __syncthreads();
 
-    if (warp == kConsumerWarps) {
-        if (lane == 0) {
-            uint32_t it = 0;
-            const char *planes = reinterpret_cast<const char *>(a.planes);
-            const int nkt = (a.nv + kTileJ - 1) / kTileJ;
-            for (;;) {
-                const unsigned long long u = atomicAdd(a.unit_counter, 1ULL);
-                if (u >= (unsigned long long) a.num_units) break;
-                // super-unit u -> (i, j-tile): prefix over i rows (it0 = first row)
-                int lo = 0, hi = a.n_it - 1;
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if ((unsigned long long) a.unit_prefix[mid] <= u) lo = mid; else hi = mid - 1;
+    uint32_t *cnts = cnt_base + tid;
+    uint32_t acc[27];
+#pragma unroll
+    for (int c = 0; c < 27; c++) acc[c] = 0;
+
+    for (uint32_t s = 0;; s++) {
+        const int st = s & 1;
+        int4 next = make_int4(-1, 0, 0, 0);
+        if (tid == 0) {
+            if (u < a.num_units) {
+                if (++chunk == nchunks) {
+                    chunk = 0;
+                    if (++cur_kt == nkt) {
+                        u += gridDim.x;
+                        if (u < a.num_units) decode();
+                    }
                 }
-                const int i = a.it0 + lo;
-                const int j0 = (a.unit_jt0[lo] + (int) (u - (unsigned long long) a.unit_prefix[lo])) * TJ;
-                // k-tiles that can hold k > j0 + 1 ... (first k is j0 + 1 at the earliest)
-                for (int kt = (j0 + 1) / kTileJ; kt < nkt; kt++) {
-                    const int k0 = kt * kTileJ;
-                    for (int b = 0; b < nblocks; b++, it++) {
-                        const int st = it % kStages;
-                        mbar_wait(&ctl->empty[st], ((it / kStages) & 1) ^ 1);
-                        ctl->meta[st] = make_int4(b, i, j0, k0);
-                        mbar_arrive_expect_tx(&ctl->full[st], ROWS * ROWW * 4);
-                        const char *src = planes + (int64_t) b * a.snp_pad * (ROWW * 4);
-                        uint32_t *dst = stage + st * STAGEW;
-                        bulk_g2s(dst, src + (int64_t) i * (ROWW * 4), ROWW * 4, &ctl->full[st]);
-                        bulk_g2s(dst + ROWW, src + (int64_t) j0 * (ROWW * 4), TJ * ROWW * 4, &ctl->full[st]);
-                        bulk_g2s(dst + (1 + TJ) * ROWW, src + (int64_t) k0 * (ROWW * 4), kTileJ * ROWW * 4, &ctl->full[st]);
+                if (u < a.num_units) next = make_int4(chunk, cur_i, cur_j0, cur_kt * kTileJ);
+            }
+            ctl->meta[(s + 1) % 3] = next;
+        }
+        __syncthreads();
+        if (tid == 0 && next.x >= 0) issue(st ^ 1, next.x, next.y, next.z, next.w);
+        const int4 meta = ctl->meta[s % 3];
+        if (meta.x < 0) break;
+        const int ch = meta.x, i = meta.y, j0 = meta.z, k0 = meta.w;
+        if (ch == 0 && warp == 0 && lane < ctl->fl.F) atomicMax(&ctl->thr[lane], __ldcg(a.gthr + lane));
+        mbar_wait(&ctl->full[st], (s >> 1) & 1);
+
+        const uint32_t *sbase = reinterpret_cast<const uint32_t *>(smem_raw + sm.stage0 + (size_t) st * sm.stage_bytes);
+        const uint32_t *irow = sbase;
+        const uint32_t *jrow = sbase + (size_t) (1 + warp) * roww;
+        const uint32_t *krow = sbase + (size_t) (1 + TJ + lane) * roww;
+        const int b_lo = ch * cb, b_hi = min(nblocks, b_lo + cb);
+
+        if constexpr (SINGLE) {
+            for (int b4 = b_lo; b4 < b_hi; b4 += 4) {
+                uint32_t pk[27];
+#pragma unroll
+                for (int c = 0; c < 27; c++) pk[c] = 0;
+                const int off = (b4 - b_lo) * 3 * BW;
+                single_block3<BW, 0>(irow + off, jrow + off, krow + off, pk);
+                single_block3<BW, 1>(irow + off, jrow + off, krow + off, pk);
+                single_block3<BW, 2>(irow + off, jrow + off, krow + off, pk);
+                single_block3<BW, 3>(irow + off, jrow + off, krow + off, pk);
+                const int k = b4 >> 2;
+#pragma unroll
+                for (int c = 0; c < 27; c++) cnts[(c * nwc + k) * nthreads] = pk[c];
+            }
+        } else {
+            for (int b = b_lo; b < b_hi; b++) {
+                const int off = (b - b_lo) * 3 * BW;
+                uint32_t pl[3][BW];
+#pragma unroll
+                for (int g = 0; g < 3; g++) load_plane<BW>(krow + off + g * BW, pl[g]);
+#pragma unroll
+                for (int ga = 0; ga < 3; ga++) {
+                    uint32_t pi[BW];
+                    load_plane<BW>(irow + off + ga * BW, pi);
+#pragma unroll
+                    for (int gb = 0; gb < 3; gb++) {
+                        uint32_t pj[BW];
+                        load_plane<BW>(jrow + off + gb * BW, pj);
+#pragma unroll
+                        for (int gc = 0; gc < 3; gc++) {
+                            const int c = ga * 9 + gb * 3 + gc;
+                            acc[c] = cell_count3_acc<BW, 1u>(pi, pj, pl[gc], acc[c]);
+                        }
+                    }
+                }
+                const unsigned d = desc[b];
+                if (d & 0x8000u) {
+                    const int seg = d & 0x7fff;
+#pragma unroll
+                    for (int c = 0; c < 27; c++) {
+                        reinterpret_cast<uint16_t *>(cnts + (c * nwc + (seg >> 1)) * nthreads)[seg & 1] = (uint16_t) acc[c];
+                        acc[c] = 0;
                     }
                 }
             }
-            const int st = it % kStages;
-            mbar_wait(&ctl->empty[st], ((it / kStages) & 1) ^ 1);
-            ctl->meta[st] = make_int4(-1, 0, 0, 0);
-            mbar_arrive(&ctl->full[st]);
         }
-    } else {
-        uint32_t *cnts = cnt_base + tid;
-        uint32_t acc[27];
-#pragma unroll
-        for (int c = 0; c < 27; c++) acc[c] = 0;
 
-        for (uint32_t it = 0;; it++) {
-            const int st = it % kStages;
-            mbar_wait(&ctl->full[st], (it / kStages) & 1);
-            const int4 meta = ctl->meta[st];
-            if (meta.x < 0) break;
-            const int b = meta.x, i = meta.y, j0 = meta.z, k0 = meta.w;
-            const uint32_t *sbase = stage + st * STAGEW;
-            const unsigned desc = a.blk_desc[b];
-            const int seg = desc & 0x7fff;
+        if (ch == nchunks - 1) {
             const int j = j0 + warp, k = k0 + lane;
-
-            uint32_t pk[3][BW];
-            {
-                const uint32_t *krow = sbase + (1 + TJ + lane) * ROWW;
-                const int swz = swizzle_of(k);
-#pragma unroll
-                for (int g = 0; g < 3; g++) load_plane<BW>(krow, g, swz, pk[g]);
+            bool valid = (i < j) && (j < k) && (k < a.nv);
+            if (valid) {
+                const uint64_t idx = triple_index((uint64_t) a.nv, (uint64_t) i, (uint64_t) j, (uint64_t) k);
+                valid = idx >= a.first && idx < a.last;
             }
-            const uint32_t *irow = sbase;
-            const uint32_t *jrow = sbase + (1 + warp) * ROWW;
-            const int swz_i = swizzle_of(i), swz_j = swizzle_of(j);
-#pragma unroll
-            for (int ga = 0; ga < 3; ga++) {
-                uint32_t pi[BW];
-                load_plane<BW>(irow, ga, swz_i, pi);
-#pragma unroll
-                for (int gb = 0; gb < 3; gb++) {
-                    uint32_t pj[BW];
-                    load_plane<BW>(jrow, gb, swz_j, pj);
-#pragma unroll
-                    for (int gc = 0; gc < 3; gc++) {
-                        const uint32_t n = cell_count3<BW>(pi, pj, pk[gc]);
-                        const int c = ga * 9 + gb * 3 + gc;
-                        if constexpr (SINGLE) store_count<CBITS>(cnts, c, nwc, seg, n);
-                        else acc[c] += n;
-                    }
-                }
-            }
-            if constexpr (!SINGLE) {
-                if (desc & 0x8000u) {
-#pragma unroll
-                    for (int c = 0; c < 27; c++) { store_count<CBITS>(cnts, c, nwc, seg, acc[c]); acc[c] = 0; }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ctl->empty[st]);
-
-            if (b == 0 && warp == 0 && lane < ctl->fl.F) atomicMax(&ctl->thr[lane], __ldcg(a.gthr + lane));
-
-            if (b == nblocks - 1) {
-                bool valid = (i < j) && (j < k) && (k < a.nv);
-                if (valid) {
-                    const uint64_t idx = triple_index((uint64_t) a.nv, (uint64_t) i, (uint64_t) j, (uint64_t) k);
-                    valid = idx >= a.first && idx < a.last;
-                }
-                combo_epilogue<27, CBITS>(ctl, a, cnts, nwc, valid, i, j, k, lane);
+            if (__any_sync(0xffffffffu, valid)) {
+                if constexpr (BALANCED) epilogue_balanced<27, SINGLE>(ctl, a, lists, cnts, nwc, nthreads, valid, i, j, k, lane);
+                else epilogue_general<27, SINGLE>(ctl, a, lists, cnts, nwc, nthreads, valid, i, j, k, lane);
             }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));
-        if (tid < ctl->fl.F) a.list_cnt[(size_t) blockIdx.x * ctl->fl.F + tid] = ctl->cnt[tid];
     }
+    search_publish(ctl, a, lists);
 }
 
 // ============================================================================
 // Merge: many partial top-N lists -> the final top-N of every fold
 // ============================================================================
-// One CTA per fold.  Entries below the global threshold cannot be in the top N;
-// the survivors are ranked by counting (tuples are unique within a fold, so the
-// canonical order is total) and written straight to their final position.
+// One CTA per fold.  Every entry gets a 128-bit key that realises the canonical
+// order (BA descending, then SNP tuple ascending) as "larger key first"; tuples are
+// unique within a fold, so keys are unique.  An MSB-first radix select (16 passes of
+// 8 bits, shared-memory histograms) finds the key of the N-th best entry; the
+// entries at or above it are then ranked by counting and written straight to their
+// final position.
 struct MergeArgs {
     const Cand *lists;          // [nlists][F][rank_in]
     const int *list_cnt;        // [nlists][F]  (nullptr: every list has rank_in entries, empty ones marked by i < 0)
-    const long long *gthr;      // [F] or nullptr
     int nlists, F, rank_in, rank_out, training;
     const FoldLayout *fl;
     void *out;                  // hpgv_epi_model_t [F][rank_out]
     int order;
-    int *sel;                   // scratch [F][nlists * rank_in]: indices of surviving entries
 };
 
 struct ModelOut {               // == hpgv_epi_model_t
@@ -541,50 +701,125 @@ struct ModelOut {               // == hpgv_epi_model_t
     uint32_t conf[4];
 };
 
-__global__ void __launch_bounds__(1024) merge_kernel(const MergeArgs m) {
-    __shared__ int nsel;
-    const int f = blockIdx.x;
-    int *sel = m.sel + (size_t) f * m.nlists * m.rank_in;
+struct Key128 {
+    unsigned long long hi, lo;
+};
+__device__ __forceinline__ bool key_ge(const Key128 &a, const Key128 &b) { return a.hi > b.hi || (a.hi == b.hi && a.lo >= b.lo); }
+__device__ __forceinline__ bool key_gt(const Key128 &a, const Key128 &b) { return a.hi > b.hi || (a.hi == b.hi && a.lo > b.lo); }
+__device__ __forceinline__ Key128 cand_key(const Cand &c, int order) {
+    Key128 k;
+    unsigned long long u = (unsigned long long) __double_as_longlong(c.ba);
+    k.hi = (u >> 63) ? ~u : (u | 0x8000000000000000ULL);             // larger BA -> larger key
+    unsigned long long t = order == 2 ? (((unsigned long long) (uint32_t) c.i << 32) | (uint32_t) c.j)
+                                      : (((unsigned long long) (uint32_t) c.i << 42) | ((unsigned long long) (uint32_t) c.j << 21) | (uint32_t) c.k);
+    k.lo = ~t;                                                        // smaller tuple -> larger key
+    return k;
+}
+__device__ __forceinline__ unsigned key_byte(const Key128 &k, int pass) {   // pass 0 = most significant byte
+    return pass < 8 ? (unsigned) (k.hi >> (56 - 8 * pass)) & 0xffu : (unsigned) (k.lo >> (56 - 8 * (pass - 8))) & 0xffu;
+}
+__device__ __forceinline__ bool key_prefix_eq(const Key128 &k, const Key128 &p, int pass) {   // the first `pass` bytes agree
+    if (pass == 0) return true;
+    if (pass < 8) return (k.hi >> (64 - 8 * pass)) == (p.hi >> (64 - 8 * pass));
+    if (k.hi != p.hi) return false;
+    if (pass == 8) return true;
+    return (k.lo >> (64 - 8 * (pass - 8))) == (p.lo >> (64 - 8 * (pass - 8)));
+}
+
+constexpr int kMergeThreads = 1024;
+
+__global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeArgs m) {
+    extern __shared__ __align__(16) uint8_t msmem[];
+    Key128 *selkey = reinterpret_cast<Key128 *>(msmem);                       // [rank_out]
+    int *selidx = reinterpret_cast<int *>(msmem + (size_t) m.rank_out * 16);   // [rank_out]
+    __shared__ unsigned hist[256];
+    __shared__ Key128 prefix;
+    __shared__ int want_sh, nsel, nvalid_sh;
+
+    const int f = blockIdx.x, tid = threadIdx.x;
     const FoldLayout &fl = *m.fl;
     const int npos = m.training ? fl.A - fl.a_in[f] : fl.a_in[f];
     const int nneg = m.training ? fl.U - fl.u_in[f] : fl.u_in[f];
     const bool degenerate = (npos == 0 || nneg == 0);
-    const long long thr = m.gthr ? m.gthr[f] : LLONG_MIN;
-    if (threadIdx.x == 0) nsel = 0;
-    __syncthreads();
     const int total = m.nlists * m.rank_in;
-    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    auto entry = [&](int e) { return m.lists + ((size_t) (e / m.rank_in) * m.F + f) * m.rank_in + (e % m.rank_in); };
+    auto entry_valid = [&](int e, Cand &c) {
         const int l = e / m.rank_in, n = e % m.rank_in;
         const int cnt = m.list_cnt ? m.list_cnt[(size_t) l * m.F + f] : m.rank_in;
-        if (n >= cnt) continue;
-        const Cand c = cand_load(m.lists + ((size_t) l * m.F + f) * m.rank_in + n);
-        if (c.i < 0) continue;
-        const long long s = degenerate ? LLONG_MIN : ba_score(c.tp, c.fp, npos, nneg);
-        if (s >= thr) sel[atomicAdd(&nsel, 1)] = e;
+        if (n >= cnt) return false;
+        c = *entry(e);
+        return c.i >= 0;
+    };
+
+    if (tid == 0) { prefix.hi = 0; prefix.lo = 0; nsel = 0; nvalid_sh = 0; }
+    __syncthreads();
+    {
+        int mine = 0;
+        for (int e = tid; e < total; e += kMergeThreads) {
+            Cand c;
+            mine += entry_valid(e, c) ? 1 : 0;
+        }
+        if (mine) atomicAdd(&nvalid_sh, mine);
     }
     __syncthreads();
-    const int ns = nsel;
-    ModelOut *out = reinterpret_cast<ModelOut *>(m.out) + (size_t) f * m.rank_out;
-    for (int t = threadIdx.x; t < ns; t += blockDim.x) {
-        const int e = sel[t];
-        const Cand c = cand_load(m.lists + ((size_t) (e / m.rank_in) * m.F + f) * m.rank_in + (e % m.rank_in));
-        int rank = 0;
-        for (int o = 0; o < ns; o++) {
-            const int e2 = sel[o];
-            const Cand d = cand_load(m.lists + ((size_t) (e2 / m.rank_in) * m.F + f) * m.rank_in + (e2 % m.rank_in));
-            rank += cand_before(d, c) ? 1 : 0;
+    const int want = min(m.rank_out, nvalid_sh);
+    if (tid == 0) want_sh = want;
+    __syncthreads();
+
+    if (want > 0) {
+        for (int pass = 0; pass < 16; pass++) {
+            for (int x = tid; x < 256; x += kMergeThreads) hist[x] = 0;
+            __syncthreads();
+            const Key128 p = prefix;
+            for (int e = tid; e < total; e += kMergeThreads) {
+                Cand c;
+                if (!entry_valid(e, c)) continue;
+                const Key128 k = cand_key(c, m.order);
+                if (key_prefix_eq(k, p, pass)) atomicAdd(&hist[key_byte(k, pass)], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int need = want_sh;               // among the entries matching the prefix we still need the `need` largest
+                int bin = 255;
+                for (; bin > 0; bin--) {
+                    if ((int) hist[bin] >= need) break;
+                    need -= (int) hist[bin];
+                }
+                want_sh = need;
+                if (pass < 8) prefix.hi |= (unsigned long long) bin << (56 - 8 * pass);
+                else prefix.lo |= (unsigned long long) bin << (56 - 8 * (pass - 8));
+            }
+            __syncthreads();
         }
-        if (rank < m.rank_out) {
-            ModelOut r;
-            r.accuracy = degenerate ? nan("") : c.ba;
-            r.snp[0] = c.i; r.snp[1] = c.j; r.snp[2] = m.order == 3 ? c.k : -1;
-            r.risky_mask = c.mask;
-            r.conf[0] = (uint32_t) c.tp; r.conf[1] = (uint32_t) (npos - c.tp);
-            r.conf[2] = (uint32_t) c.fp; r.conf[3] = (uint32_t) (nneg - c.fp);
-            out[rank] = r;
+        // prefix is now the key of the want-th best entry: collect everything at or above it
+        const Key128 kth = prefix;
+        for (int e = tid; e < total; e += kMergeThreads) {
+            Cand c;
+            if (!entry_valid(e, c)) continue;
+            const Key128 k = cand_key(c, m.order);
+            if (key_ge(k, kth)) {
+                const int pos = atomicAdd(&nsel, 1);
+                if (pos < m.rank_out) { selkey[pos] = k; selidx[pos] = e; }
+            }
         }
     }
-    for (int t = (ns < m.rank_out ? ns : m.rank_out) + threadIdx.x; t < m.rank_out; t += blockDim.x) {
+    __syncthreads();
+    const int ns = min(nsel, m.rank_out);
+    ModelOut *out = reinterpret_cast<ModelOut *>(m.out) + (size_t) f * m.rank_out;
+    for (int t = tid; t < ns; t += kMergeThreads) {
+        const Key128 k = selkey[t];
+        int rank = 0;
+        for (int o = 0; o < ns; o++) rank += key_gt(selkey[o], k) ? 1 : 0;
+        const Cand c = *entry(selidx[t]);
+        ModelOut r;
+        r.accuracy = degenerate ? nan("") : c.ba;
+        r.snp[0] = c.i; r.snp[1] = c.j; r.snp[2] = m.order == 3 ? c.k : -1;
+        r.risky_mask = c.mask;
+        r.conf[0] = (uint32_t) c.tp; r.conf[1] = (uint32_t) (npos - c.tp);
+        r.conf[2] = (uint32_t) c.fp; r.conf[3] = (uint32_t) (nneg - c.fp);
+        out[rank] = r;
+    }
+    for (int t = ns + tid; t < m.rank_out; t += kMergeThreads) {
         ModelOut r;
         r.accuracy = nan("");
         r.snp[0] = r.snp[1] = r.snp[2] = -1;
@@ -609,7 +844,6 @@ __global__ void models_to_cands_kernel(const ModelOut *in, int64_t n, Cand *out)
 // ============================================================================
 // Parity hook: explicit combinations, one warp each (simple on purpose)
 // ============================================================================
-template <int BW>
 __global__ void eval_kernel(const uint32_t *__restrict__ planes, const uint16_t *__restrict__ blk_desc,
                             const FoldLayout *__restrict__ flp, int64_t snp_pad, int order, int training,
                             int64_t ncomb, const int32_t *__restrict__ combs,
@@ -617,6 +851,7 @@ __global__ void eval_kernel(const uint32_t *__restrict__ planes, const uint16_t 
     extern __shared__ int segcnt_all[];                 // [warps][nseg][C]
     const FoldLayout &fl = *flp;
     const int C = order == 2 ? 9 : 27;
+    const int bw = fl.bw;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t comb = (int64_t) blockIdx.x * (blockDim.x >> 5) + wib;
     int *segcnt = segcnt_all + (size_t) wib * fl.nseg * C;
@@ -627,16 +862,15 @@ __global__ void eval_kernel(const uint32_t *__restrict__ planes, const uint16_t 
     for (int o = 0; o < order; o++) s[o] = combs[comb * order + o];
     for (int b = 0; b < fl.nblocks; b++) {
         const int seg = blk_desc[b] & 0x7fff;
-        for (int x = lane; x < C * BW; x += 32) {
-            const int c = x / BW, w = x % BW;
+        if (seg >= fl.nseg) continue;                   // padding block of the single-block layout
+        for (int x = lane; x < C * bw; x += 32) {
+            const int c = x / bw, w = x % bw;
             uint32_t v = 0xffffffffu;
             int rem = c;
             for (int o = order - 1; o >= 0; o--) {
                 const int g = rem % 3;
                 rem /= 3;
-                int wp = w;
-                if (BW == 8) wp = (((w >> 2) ^ swizzle_of(s[o])) << 2) | (w & 3);
-                v &= planes[(((int64_t) b * snp_pad + s[o]) * 3 + g) * BW + wp];
+                v &= planes[plane_word(fl, snp_pad, b, s[o], g, w)];
             }
             atomicAdd(&segcnt[seg * C + c], __popc(v));
         }

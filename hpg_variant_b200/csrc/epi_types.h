@@ -6,25 +6,37 @@ namespace hpgv {
 
 constexpr int kMaxFolds  = 32;            // HPGV_MAX_FOLDS
 constexpr int kMaxSegs   = 2 * kMaxFolds; // one segment per (fold, class)
-constexpr int kMaxBlocks = 8192;          // sample-axis blocks per SNP row
+constexpr int kMaxBlocks = 4096;          // sample-axis blocks per SNP row (256 samples each when segments span blocks)
 constexpr int kMaxRank   = 4096;          // HPGV_MAX_RANK
 constexpr int kTileJ     = 32;            // one j (or k) SNP per lane
+constexpr int kMaxWarps  = 16;            // consumer warps per CTA = i (or j) rows per tile
 
 // Per-fold sizes and the segmented sample layout chosen by set_folds().
 //
 // Samples are permuted to (fold, class) order: segment s = 2*fold + cls
-// (cls 0 = affected, 1 = unaffected) is a run of `blocks` of BW 32-bit words;
-// every bit position holds one sample of that segment or padding (never set in
-// any plane).  Because a sample is in exactly one fold, the per-fold TRAINING
-// table of the reference (model.c:131-206) is total - in-fold.
+// (cls 0 = affected, 1 = unaffected).  A segment is a run of blocks; a block is
+// bw 32-bit words of each of the three genotype planes; every bit position
+// holds one sample of that segment or padding (never set in any plane).
+// Because a sample is in exactly one fold, the per-fold TRAINING table of the
+// reference (model.c:131-206) is total - in-fold.
+//
+// Blocks are grouped into chunks of cb blocks; the packed planes are stored
+// chunk-major, [chunk][snp][row_words] with row_words = cb*3*bw (+ padding so
+// that row_words/4 is odd: 32 lanes reading 32 consecutive rows with LDS.128
+// then hit 8 distinct 16-byte bank groups per quarter-warp).  Inside a row:
+// word (bl, g, w) at (bl*3 + g)*bw + w.
 struct FoldLayout {
     int F;                 // folds
     int nseg;              // 2F
-    int nblocks;           // total blocks along the sample axis
-    int bw;                // words per block (4 or 8)
     int A, U;              // dataset-level class sizes (used by the high-risk rule, epistasis.c:37)
     int balanced;          // A == U: the float32 rule collapses to an integer test
     float ratio;           // (float)A / (float)U, mdr.c:52
+    int bw;                // words per plane per block (4 or 8)
+    int single;            // 1: every segment is exactly one block (block b <-> segment b, byte counters)
+    int nblocks;           // real blocks along the sample axis (single: nseg rounded up to a multiple of 4)
+    int cb;                // blocks per chunk (single: multiple of 4)
+    int nchunks;
+    int row_words;         // words per chunk row
     int a_in[kMaxFolds];   // cases in fold f (its testing part)
     int u_in[kMaxFolds];
 };
@@ -40,20 +52,20 @@ static_assert(sizeof(Cand) == 32, "Cand must be 32 bytes");
 
 // Arguments of the order-2 / order-3 search kernels.
 struct SearchArgs {
-    const uint32_t *planes;     // [nblocks][snp_pad][3][bw]
+    const uint32_t *planes;     // [nchunks][snp_pad][row_words]
     const uint16_t *blk_desc;   // [nblocks] segment id | 0x8000 when last block of its segment
     const FoldLayout *fl;
-    int64_t snp_pad;            // padded SNP rows per block
+    int64_t snp_pad;            // padded SNP rows per chunk
     int nv;                     // real SNP count
     int training;               // evaluate on the training (1) or testing (0) part
     int rank;                   // N
+    int lists_in_smem;          // per-CTA top-N lists live in shared memory during the search
     uint64_t first, last;       // linear combination index range
-    // work list: order 2 -> unit = (i-tile, j-tile); prefix[t] = units before i-tile t0+t
+    // work list: order 2 -> unit = (i-tile, j-tile); order 3 -> unit = (i, j-tile); prefix[t] = units before row-group t
     const int64_t *unit_prefix;
-    const int32_t *unit_jt0;    // first j-tile of each i-tile
-    int it0, n_it;              // first i-tile, number of i-tiles
+    const int32_t *unit_jt0;    // first j-tile of each row group
+    int it0, n_it;              // first row group, number of row groups
     int64_t num_units;
-    unsigned long long *unit_counter;
     // per-CTA candidate lists
     Cand *lists;                // [grid][F][rank]
     int *list_cnt;              // [grid][F]

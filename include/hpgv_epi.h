@@ -150,6 +150,7 @@ typedef struct {
     int count_bits;                                          /* 8 or 16: per-segment counter width in shared memory */
     int64_t plane_bytes;                                     /* bytes of the packed planes in HBM */
     int words_per_class_row;                                 /* W of SURVEY 8(d): ceil(A/32)+ceil(U/32) */
+    int num_chunks, chunk_blocks, row_words;                 /* planes are [chunk][snp][row_words], chunk = chunk_blocks blocks */
 } hpgv_epi_layout_t;
 int hpgv_epi_layout(const hpgv_epi_ctx *ctx, hpgv_epi_layout_t *out);
 
