@@ -23,6 +23,7 @@
 // training table (total - in-fold), the exact high-risk mask, TP/FP and an integer
 // score, and offers tuples that beat the running threshold to the CTA's top-N list.
 #pragma once
+#include <type_traits>
 #include "epi_device.cuh"
 
 namespace hpgv {
@@ -181,6 +182,10 @@ __device__ __forceinline__ void offer_fold(SearchCtl *ctl, const SearchArgs &a, 
     const long long thr = *reinterpret_cast<volatile long long *>(&ctl->thr[f]);
     unsigned want = __ballot_sync(0xffffffffu, valid && score >= thr);
     while (want) {
+        // the threshold rises while the warp works through its lanes: drop the lanes that no longer reach it
+        const long long now = *reinterpret_cast<volatile long long *>(&ctl->thr[f]);
+        want &= __ballot_sync(0xffffffffu, score >= now);
+        if (!want) break;
         const int src = __ffs(want) - 1;
         want &= want - 1;
         Cand c;
@@ -248,6 +253,15 @@ __device__ __forceinline__ void epilogue_general(SearchCtl *ctl, const SearchArg
     }
 }
 
+// compile-time loop: f(std::integral_constant<int, 0>{}) ... f(std::integral_constant<int, N - 1>{})
+template <int N, int I = 0, typename Fn>
+__device__ __forceinline__ void static_for(Fn &&f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<N, I + 1>(f);
+    }
+}
+
 // d = c + a.u16[0] * b.s8[0] + a.u16[1] * b.s8[1]
 __device__ __forceinline__ int dp2a_lo_us(uint32_t a16x2, uint32_t b8, int c) {
     int d;
@@ -255,25 +269,38 @@ __device__ __forceinline__ int dp2a_lo_us(uint32_t a16x2, uint32_t b8, int c) {
     return d;
 }
 
+// risky = (trA >= trU) && (pair != 0); when risky: tpfp += ev, mask |= bit  (four instructions, two of them predicated)
+template <uint32_t BIT>
+__device__ __forceinline__ void risk_accumulate(int d, uint32_t tr, uint32_t ev, uint32_t &tpfp, uint32_t &mask) {
+    asm("{\n"
+        ".reg .pred p;\n"
+        "setp.ge.s32 p, %2, 0;\n"
+        "setp.ne.and.u32 p, %3, 0, p;\n"
+        "@p add.u32 %0, %0, %4;\n"
+        "@p or.b32 %1, %1, %5;\n"
+        "}\n"
+        : "+r"(tpfp), "+r"(mask)
+        : "r"(d), "r"(tr), "r"(ev), "n"(BIT));
+}
+
 // one fold of the balanced epilogue; in_of(c) returns the in-fold pair (cases | controls << 16) of cell c
-template <int NCELLS, typename InOf>
+template <int NCELLS, bool TRAINING, typename InOf>
 __device__ __forceinline__ void balanced_fold(SearchCtl *ctl, const SearchArgs &a, Cand *lists, const uint32_t (&tot)[NCELLS], int f,
                                               InOf in_of, bool valid, int si, int sj, int sk, int lane) {
     const FoldLayout &fl = ctl->fl;
     uint32_t tpfp = 0, mask = 0;
-#pragma unroll
-    for (int c = 0; c < NCELLS; c++) {
+    auto cell = [&](auto cc) {
+        constexpr int c = decltype(cc)::value;
         const uint32_t in = in_of(c);
         const uint32_t tr = tot[c] - in;                     // no borrow: every half of tot >= the half of in
         const int d = dp2a_lo_us(tr, 0x0000FF01u, 0);        // trA - trU
-        const bool r = (d >= 0) && (tr != 0);                // d >= 0 and trA == 0 imply trU == 0
-        const uint32_t ev = a.training ? tr : in;
-        tpfp += r ? ev : 0u;
-        mask |= (r ? 1u : 0u) << c;
-    }
+        // d >= 0 and trA == 0 imply trU == 0, so "tr != 0" is the reference's "cell not empty" (0/0 = NaN is low risk)
+        risk_accumulate<(1u << c)>(d, tr, TRAINING ? tr : in, tpfp, mask);
+    };
+    static_for<NCELLS>(cell);
     const int tp = (int) (tpfp & 0xffffu), fp = (int) (tpfp >> 16);
-    const int npos = a.training ? fl.A - fl.a_in[f] : fl.a_in[f];
-    const int nneg = a.training ? fl.U - fl.u_in[f] : fl.u_in[f];
+    const int npos = TRAINING ? fl.A - fl.a_in[f] : fl.a_in[f];
+    const int nneg = TRAINING ? fl.U - fl.u_in[f] : fl.u_in[f];
     const bool degenerate = (npos == 0 || nneg == 0);
     const long long score = degenerate ? LLONG_MIN : ba_score(tp, fp, npos, nneg);
     offer_fold(ctl, a, lists, f, valid, score, degenerate, npos, nneg, si, sj, sk, mask, tp, fp, lane);
@@ -282,9 +309,9 @@ __device__ __forceinline__ void balanced_fold(SearchCtl *ctl, const SearchArgs &
 // Fast version for balanced data sets (A == U <= 65535): every count pair travels as
 // one register (cases | controls << 16); r = A/U = 1 makes the float32 rule exact,
 // risky <=> trA >= trU and trA > 0 (see high_risk()).
-template <int NCELLS, bool U8>
-__device__ __forceinline__ void epilogue_balanced(SearchCtl *ctl, const SearchArgs &a, Cand *lists, const uint32_t *cnts, int nwc,
-                                                  int nthreads, bool valid, int si, int sj, int sk, int lane) {
+template <int NCELLS, bool U8, bool TRAINING>
+__device__ __forceinline__ void epilogue_balanced_t(SearchCtl *ctl, const SearchArgs &a, Cand *lists, const uint32_t *cnts, int nwc,
+                                                    int nthreads, bool valid, int si, int sj, int sk, int lane) {
     const int nfolds = ctl->fl.F;
     uint32_t tot[NCELLS];                     // total cases | total controls << 16
     if constexpr (U8) {
@@ -305,9 +332,9 @@ __device__ __forceinline__ void epilogue_balanced(SearchCtl *ctl, const SearchAr
             uint32_t w[NCELLS];
 #pragma unroll
             for (int c = 0; c < NCELLS; c++) w[c] = cnts[(c * nwc + k) * nthreads];
-            balanced_fold<NCELLS>(ctl, a, lists, tot, 2 * k, [&](int c) { return __byte_perm(w[c], 0u, 0x4240); }, valid, si, sj, sk, lane);
+            balanced_fold<NCELLS, TRAINING>(ctl, a, lists, tot, 2 * k, [&](int c) { return __byte_perm(w[c], 0u, 0x4240); }, valid, si, sj, sk, lane);
             if (2 * k + 1 < nfolds)
-                balanced_fold<NCELLS>(ctl, a, lists, tot, 2 * k + 1, [&](int c) { return __byte_perm(w[c], 0u, 0x4341); }, valid, si, sj, sk, lane);
+                balanced_fold<NCELLS, TRAINING>(ctl, a, lists, tot, 2 * k + 1, [&](int c) { return __byte_perm(w[c], 0u, 0x4341); }, valid, si, sj, sk, lane);
         }
     } else {
 #pragma unroll
@@ -317,8 +344,14 @@ __device__ __forceinline__ void epilogue_balanced(SearchCtl *ctl, const SearchAr
             for (int c = 0; c < NCELLS; c++) tot[c] += cnts[(c * nwc + k) * nthreads];
         }
         for (int f = 0; f < nfolds; f++)
-            balanced_fold<NCELLS>(ctl, a, lists, tot, f, [&](int c) { return cnts[(c * nwc + f) * nthreads]; }, valid, si, sj, sk, lane);
+            balanced_fold<NCELLS, TRAINING>(ctl, a, lists, tot, f, [&](int c) { return cnts[(c * nwc + f) * nthreads]; }, valid, si, sj, sk, lane);
     }
+}
+template <int NCELLS, bool U8>
+__device__ __forceinline__ void epilogue_balanced(SearchCtl *ctl, const SearchArgs &a, Cand *lists, const uint32_t *cnts, int nwc,
+                                                  int nthreads, bool valid, int si, int sj, int sk, int lane) {
+    if (a.training) epilogue_balanced_t<NCELLS, U8, true>(ctl, a, lists, cnts, nwc, nthreads, valid, si, sj, sk, lane);
+    else epilogue_balanced_t<NCELLS, U8, false>(ctl, a, lists, cnts, nwc, nthreads, valid, si, sj, sk, lane);
 }
 
 // shift of the byte counter of block q (0..3) of a four-block group: segments (2k A, 2k U, 2k+1 A, 2k+1 U)
