@@ -76,12 +76,12 @@ __global__ void unpack_masks_kernel(const uint32_t *__restrict__ planes, int64_t
 // Shared pieces of the search kernels
 // ============================================================================
 struct __align__(16) SearchCtl {
-    uint64_t full[2];              // one mbarrier per stage
+    uint64_t full[2];              // per stage: the chunk rows have landed
+    uint64_t empty[2];             // per stage: every warp is done reading it
     int4 meta[3];                  // step descriptors: x = chunk (-1: no more work), y/z/w = tile origins
     long long thr[kMaxFolds];      // score a candidate must reach to be offered to the list
     int lock[kMaxFolds];
     int cnt[kMaxFolds];
-    int min_idx[kMaxFolds];
     FoldLayout fl;
 };
 
@@ -104,74 +104,65 @@ __host__ __device__ inline SmemMap search_smem_map(const FoldLayout &fl, int row
 }
 
 // ---- top-N list maintenance (one list per CTA and fold) ------------------------
-// Called by a full warp with a warp-uniform candidate.  Replaces
-// add_to_model_ranking (model.c:481-521) with a deterministic order.
+// Replaces add_to_model_ranking (model.c:481-521) with a deterministic order.  A
+// list that has reached N entries is kept as a binary heap whose root is the entry
+// that ranks LAST in the canonical order, so an offer is one comparison with the
+// root and, when it wins, one sift-down.  Lane 0 does the work under the fold's
+// lock; the candidate is warp-uniform.
+__device__ __forceinline__ void heap_sift_down(Cand *list, int n, int i, const Cand &c) {
+    // place c at or below position i: children that rank after c move up
+    for (;;) {
+        int w = 2 * i + 1;
+        if (w >= n) break;
+        Cand cw = cand_load(list + w);
+        if (w + 1 < n) {
+            const Cand cr = cand_load(list + w + 1);
+            if (cand_before(cw, cr)) { cw = cr; w = w + 1; }      // the right child ranks after the left one
+        }
+        if (!cand_before(c, cw)) break;                           // c ranks after both children: it stays here
+        cand_store(list + i, cw);
+        i = w;
+    }
+    cand_store(list + i, c);
+}
+
 __device__ __forceinline__ void warp_offer(SearchCtl *ctl, const SearchArgs &a, Cand *lists, int f, const Cand &c, int lane) {
     if (lane == 0) {
         while (atomicCAS(&ctl->lock[f], 0, 1) != 0) __nanosleep(20);
-    }
-    __syncwarp();
-    __threadfence_block();
-    Cand *list = lists + (size_t) f * a.rank;
-    // every lane reads the list state BEFORE lane 0 modifies it, so the decisions below are warp-uniform
-    const int cnt = *reinterpret_cast<volatile int *>(&ctl->cnt[f]);
-    bool replace = false;
-    int mi = 0;
-    if (cnt >= a.rank) {
-        mi = *reinterpret_cast<volatile int *>(&ctl->min_idx[f]);
-        const Cand worst = cand_load(list + mi);
-        replace = cand_before(c, worst);
-    }
-    __syncwarp();
-    bool rescan;
-    if (cnt < a.rank) {
-        if (lane == 0) {
+        __threadfence_block();
+        Cand *list = lists + (size_t) f * a.rank;
+        const int cnt = *reinterpret_cast<volatile int *>(&ctl->cnt[f]);
+        bool new_root = false;
+        if (cnt < a.rank) {
             cand_store(list + cnt, c);
             *reinterpret_cast<volatile int *>(&ctl->cnt[f]) = cnt + 1;
+            if (cnt + 1 == a.rank) {
+                for (int i = a.rank / 2 - 1; i >= 0; i--) {       // Floyd heap construction
+                    const Cand x = cand_load(list + i);
+                    heap_sift_down(list, a.rank, i, x);
+                }
+                new_root = true;
+            }
+        } else {
+            const Cand root = cand_load(list);
+            if (cand_before(c, root)) {
+                heap_sift_down(list, a.rank, 0, c);
+                new_root = true;
+            }
         }
-        rescan = (cnt + 1 == a.rank);
-    } else {
-        if (replace && lane == 0) cand_store(list + mi, c);
-        rescan = replace;
-    }
-    __syncwarp();
-    if (rescan) {
-        // list is full: find the entry that ranks last; its score is the new threshold
-        __threadfence_block();
-        // sentinel that ranks before every real entry, so lanes without an entry never win
-        Cand w;
-        w.ba = INFINITY; w.i = -1; w.j = -1; w.k = -1; w.mask = 0; w.tp = 0; w.fp = 0;
-        int widx = -1;
-        for (int e = lane; e < a.rank; e += 32) {
-            Cand x = cand_load(list + e);
-            if (cand_before(w, x)) { w = x; widx = e; }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            Cand o;
-            o.ba = __shfl_xor_sync(0xffffffffu, w.ba, off);
-            o.i = __shfl_xor_sync(0xffffffffu, w.i, off);
-            o.j = __shfl_xor_sync(0xffffffffu, w.j, off);
-            o.k = __shfl_xor_sync(0xffffffffu, w.k, off);
-            o.tp = __shfl_xor_sync(0xffffffffu, w.tp, off);
-            o.fp = __shfl_xor_sync(0xffffffffu, w.fp, off);
-            o.mask = 0;
-            const int oidx = __shfl_xor_sync(0xffffffffu, widx, off);
-            if (cand_before(w, o)) { w = o; widx = oidx; }
-        }
-        if (lane == 0) {
+        if (new_root) {
+            // the root ranks last: its score is the threshold an offer must reach from now on
+            const Cand root = cand_load(list);
             const FoldLayout &fl = ctl->fl;
             const int npos = a.training ? fl.A - fl.a_in[f] : fl.a_in[f];
             const int nneg = a.training ? fl.U - fl.u_in[f] : fl.u_in[f];
-            long long s = (npos == 0 || nneg == 0) ? LLONG_MIN : ba_score(w.tp, w.fp, npos, nneg);
-            *reinterpret_cast<volatile int *>(&ctl->min_idx[f]) = widx;
-            atomicMax(&ctl->thr[f], s);
-            atomicMax(a.gthr + f, s);
+            const long long sc = (npos == 0 || nneg == 0) ? LLONG_MIN : ba_score(root.tp, root.fp, npos, nneg);
+            atomicMax(&ctl->thr[f], sc);
+            atomicMax(a.gthr + f, sc);
         }
+        __threadfence_block();
+        atomicExch(&ctl->lock[f], 0);
     }
-    __syncwarp();
-    __threadfence_block();
-    if (lane == 0) atomicExch(&ctl->lock[f], 0);
     __syncwarp();
 }
 
@@ -403,10 +394,12 @@ __device__ __forceinline__ void search_init(SearchCtl *ctl, const SearchArgs &a,
     if (tid == 0) {
         mbar_init(&ctl->full[0], 1);
         mbar_init(&ctl->full[1], 1);
+        mbar_init(&ctl->empty[0], blockDim.x >> 5);
+        mbar_init(&ctl->empty[1], blockDim.x >> 5);
         mbar_fence_init();
         ctl->fl = *a.fl;
     }
-    if (tid < kMaxFolds) { ctl->thr[tid] = LLONG_MIN; ctl->lock[tid] = 0; ctl->cnt[tid] = 0; ctl->min_idx[tid] = 0; }
+    if (tid < kMaxFolds) { ctl->thr[tid] = LLONG_MIN; ctl->lock[tid] = 0; ctl->cnt[tid] = 0; }
     for (size_t x = tid; x < cnt_words; x += blockDim.x) cnt_base[x] = 0;   // halves that are never written must read 0
     if constexpr (!SINGLE) {
         const int nb = a.fl->nblocks;
@@ -463,13 +456,16 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
         bulk_g2s(dst, src + (int64_t) i0 * row_bytes, (uint32_t) TI * row_bytes, &ctl->full[st]);
         bulk_g2s(dst + (size_t) TI * row_bytes, src + (int64_t) j0 * row_bytes, (uint32_t) kTileJ * row_bytes, &ctl->full[st]);
     };
-    if (tid == 0) {
+    // the producer is lane 0 of the LAST warp: it issues the copies of step s + 1 at the top of its own step s
+    const bool producer = (tid == nthreads - 32);
+    if (producer) {
         if (u < a.num_units) {
             decode();
             ctl->meta[0] = make_int4(0, cur_i0, cur_j0, 0);
             issue(0, 0, cur_i0, cur_j0);
         } else {
             ctl->meta[0] = make_int4(-1, 0, 0, 0);
+            mbar_arrive(&ctl->full[0]);
         }
     }
 
@@ -480,8 +476,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
 
     for (uint32_t s = 0;; s++) {
         const int st = s & 1;
-        int4 next = make_int4(-1, 0, 0, 0);
-        if (tid == 0) {
+        if (producer) {
+            int4 next = make_int4(-1, 0, 0, 0);
             if (u < a.num_units) {
                 // the step after this one
                 if (++chunk == nchunks) {
@@ -492,14 +488,16 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
                 if (u < a.num_units) next = make_int4(chunk, cur_i0, cur_j0, 0);
             }
             ctl->meta[(s + 1) % 3] = next;
+            if (s >= 1) mbar_wait(&ctl->empty[st ^ 1], ((s - 1) >> 1) & 1);   // every warp has read step s - 1
+            if (next.x >= 0) issue(st ^ 1, next.x, next.y, next.z);
+            else mbar_arrive(&ctl->full[st ^ 1]);                              // end marker: a phase without data
         }
-        __syncthreads();                       // everyone is done with step s-1: its stage may be overwritten
-        if (tid == 0 && next.x >= 0) issue(st ^ 1, next.x, next.y, next.z);
+        __syncwarp();
+        mbar_wait(&ctl->full[st], (s >> 1) & 1);
         const int4 meta = ctl->meta[s % 3];
         if (meta.x < 0) break;
         const int ch = meta.x, i0 = meta.y, j0 = meta.z;
         if (ch == 0 && warp == 0 && lane < ctl->fl.F) atomicMax(&ctl->thr[lane], __ldcg(a.gthr + lane));
-        mbar_wait(&ctl->full[st], (s >> 1) & 1);
 
         const uint32_t *sbase = reinterpret_cast<const uint32_t *>(smem_raw + sm.stage0 + (size_t) st * sm.stage_bytes);
         const uint32_t *irow = sbase + (size_t) warp * roww;
@@ -544,6 +542,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
                 }
             }
         }
+
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->empty[st]);        // this warp is done with the stage
 
         if (ch == nchunks - 1) {
             const int i = i0 + warp, j = j0 + lane;
@@ -601,13 +602,15 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3_kernel(const Search
         bulk_g2s(dst + (size_t) (1 + TJ) * row_bytes, src + (int64_t) k0 * row_bytes, (uint32_t) kTileJ * row_bytes, &ctl->full[st]);
     };
     // meta: x = chunk, y = i, z = j0, w = k0
-    if (tid == 0) {
+    const bool producer = (tid == nthreads - 32);
+    if (producer) {
         if (u < a.num_units) {
             decode();
             ctl->meta[0] = make_int4(0, cur_i, cur_j0, cur_kt * kTileJ);
             issue(0, 0, cur_i, cur_j0, cur_kt * kTileJ);
         } else {
             ctl->meta[0] = make_int4(-1, 0, 0, 0);
+            mbar_arrive(&ctl->full[0]);
         }
     }
 
@@ -618,8 +621,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3_kernel(const Search
 
     for (uint32_t s = 0;; s++) {
         const int st = s & 1;
-        int4 next = make_int4(-1, 0, 0, 0);
-        if (tid == 0) {
+        if (producer) {
+            int4 next = make_int4(-1, 0, 0, 0);
             if (u < a.num_units) {
                 if (++chunk == nchunks) {
                     chunk = 0;
@@ -631,14 +634,16 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3_kernel(const Search
                 if (u < a.num_units) next = make_int4(chunk, cur_i, cur_j0, cur_kt * kTileJ);
             }
             ctl->meta[(s + 1) % 3] = next;
+            if (s >= 1) mbar_wait(&ctl->empty[st ^ 1], ((s - 1) >> 1) & 1);
+            if (next.x >= 0) issue(st ^ 1, next.x, next.y, next.z, next.w);
+            else mbar_arrive(&ctl->full[st ^ 1]);
         }
-        __syncthreads();
-        if (tid == 0 && next.x >= 0) issue(st ^ 1, next.x, next.y, next.z, next.w);
+        __syncwarp();
+        mbar_wait(&ctl->full[st], (s >> 1) & 1);
         const int4 meta = ctl->meta[s % 3];
         if (meta.x < 0) break;
         const int ch = meta.x, i = meta.y, j0 = meta.z, k0 = meta.w;
         if (ch == 0 && warp == 0 && lane < ctl->fl.F) atomicMax(&ctl->thr[lane], __ldcg(a.gthr + lane));
-        mbar_wait(&ctl->full[st], (s >> 1) & 1);
 
         const uint32_t *sbase = reinterpret_cast<const uint32_t *>(smem_raw + sm.stage0 + (size_t) st * sm.stage_bytes);
         const uint32_t *irow = sbase;
@@ -692,6 +697,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3_kernel(const Search
                 }
             }
         }
+
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->empty[st]);
 
         if (ch == nchunks - 1) {
             const int j = j0 + warp, k = k0 + lane;
