@@ -36,7 +36,7 @@ def _env():
 
 def build(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
     inc = [os.path.join(os.path.dirname(HERE), "include", "hpgv_epi.h")]
     if force or _newer(LIB, srcs + inc):
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "epi_capi.cu")]
@@ -47,8 +47,8 @@ def build(force=False, verbose=False):
     if os.path.exists(host_src):
         compat = os.path.join(os.path.dirname(HERE), "include", "hpgv_epi_compat.h")
         if force or _newer(HOSTLIB, [host_src, compat] + inc + [LIB]):
-            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", HOSTLIB, host_src,
-                            "-L" + HERE, "-lhpgv_epi", "-Wl,-rpath,$ORIGIN"], check=True, env=_env())
+            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I/usr/local/cuda/include", "-o", HOSTLIB, host_src,
+                            "-L" + HERE, "-lhpgv_epi", "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath,$ORIGIN"], check=True, env=_env())
         cli_src = os.path.join(CSRC, "epi_cli.cpp")
         if os.path.exists(cli_src) and (force or _newer(CLI, [cli_src, HOSTLIB])):
             subprocess.run(["g++", "-O2", "-std=c++17", "-o", CLI, cli_src, "-L" + HERE, "-lhpgv_epi_host", "-lhpgv_epi",

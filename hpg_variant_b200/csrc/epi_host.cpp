@@ -1,0 +1,617 @@
+// epi_host.cpp -- the reference's C host API for `hpg-var-gwas epi` (include/hpgv_epi_compat.h),
+// re-provided on top of the CUDA engine (include/hpgv_epi.h).  Host-side plumbing only: option
+// handling, the dataset mmap, fold drawing, the repetition loop, the CV-C / CV-A merge of the
+// per-fold rankings and the .epi report.  Every count, risk flag, accuracy and per-fold ranking
+// comes from the GPU; nothing in this file evaluates a SNP combination.
+#include "../../include/hpgv_epi_compat.h"
+#include "../../include/hpgv_epi.h"
+
+#include <cuda_runtime_api.h>
+#include <errno.h>
+#include <fcntl.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <sys/time.h>
+#include <time.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <string>
+#include <vector>
+
+// -------------------------------------------------------------------------------------
+// logging in the reference's format (lib/c/src/commons/log.c:19-39): "<ctime>\t<LEVEL>\t<file> [<line>] in <func>(): <msg>",
+// INFO and below to stdout, WARNING and above to stderr, everything also to hpg-var-gwas.log when it could be opened
+// -------------------------------------------------------------------------------------
+namespace {
+
+enum { LV_DEBUG = 1, LV_INFO = 2, LV_WARN = 3, LV_ERROR = 4, LV_FATAL = 5 };
+int g_log_level = LV_INFO;
+FILE *g_log_file = nullptr;
+
+void log_msg(int level, const char *word, const char *file, int line, const char *func, const char *fmt, ...) {
+    if (level < g_log_level) return;
+    time_t raw;
+    time(&raw);
+    char stamp[64];
+    snprintf(stamp, sizeof stamp, "%s", ctime(&raw));
+    stamp[strcspn(stamp, "\n")] = 0;
+    char body[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(body, sizeof body, fmt, ap);
+    va_end(ap);
+    FILE *os = level < LV_WARN ? stdout : stderr;
+    fprintf(os, "%s\t%s\t%s [%i] in %s(): %s", stamp, word, file, line, func, body);
+    if (g_log_file) fprintf(g_log_file, "%s\t%s\t%s [%i] in %s(): %s", stamp, word, file, line, func, body);
+}
+#define LOGI(...) log_msg(LV_INFO, "INFO", "epi_host.cpp", __LINE__, __func__, __VA_ARGS__)
+#define LOGW(...) log_msg(LV_WARN, "WARNING", "epi_host.cpp", __LINE__, __func__, __VA_ARGS__)
+#define LOGE(...) log_msg(LV_ERROR, "ERROR", "epi_host.cpp", __LINE__, __func__, __VA_ARGS__)
+#define LOGF(...) do { log_msg(LV_FATAL, "FATAL", "epi_host.cpp", __LINE__, __func__, __VA_ARGS__); exit(1); } while (0)
+
+long env_long(const char *name, long dflt) {
+    const char *v = getenv(name);
+    return (v && *v) ? strtol(v, nullptr, 10) : dflt;
+}
+
+long clock_seed() {      // what array_shuffle_int seeds with (lib/c/src/math/data/array_utils.c:176-179)
+    struct timeval tv;
+    gettimeofday(&tv, nullptr);
+    return (long) tv.tv_usec;
+}
+
+}  // namespace
+
+// -------------------------------------------------------------------------------------
+// dataset: dataset.c:54-72
+// -------------------------------------------------------------------------------------
+extern "C" uint8_t *epistasis_dataset_load(int *num_affected, int *num_unaffected, size_t *num_variants, size_t *file_len,
+                                           size_t *genotypes_offset, char *filename) {
+    const int fd = open(filename, O_RDONLY);
+    if (fd < 0) return nullptr;
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || sb.st_size < 12) { close(fd); return nullptr; }
+    void *map = mmap(nullptr, (size_t) sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (map == MAP_FAILED) return nullptr;
+    const uint8_t *p = static_cast<const uint8_t *>(map);
+    const long long len = sb.st_size;
+    uint32_t h[4] = {0, 0, 0, 0};
+    memcpy(h, p, len >= 16 ? 16 : 12);
+    auto fits = [&](long long n, long long a, long long u, long long off, long long slack) {
+        return n >= 1 && a >= 1 && u >= 1 && len >= off + n * (a + u) && len <= off + n * (a + u) + slack;
+    };
+    // current header: 3 x uint32 (dataset.c:58-63); the shipped fixture has size_t + 2 x uint32
+    if (fits(h[0], h[1], h[2], 12, 0)) { *num_variants = h[0]; *num_affected = (int) h[1]; *num_unaffected = (int) h[2]; *genotypes_offset = 12; }
+    else if (len >= 16 && h[1] == 0 && fits(h[0], h[2], h[3], 16, 7)) { *num_variants = h[0]; *num_affected = (int) h[2]; *num_unaffected = (int) h[3]; *genotypes_offset = 16; }
+    else { *num_variants = h[0]; *num_affected = (int) h[1]; *num_unaffected = (int) h[2]; *genotypes_offset = 12; }   // what the reference would read
+    *file_len = (size_t) len;
+    return static_cast<uint8_t *>(map);
+}
+
+extern "C" int epistasis_dataset_close(uint8_t *contents, size_t file_len) {
+    if (!contents || file_len == 0) return -1;
+    return munmap(contents, file_len);
+}
+
+// -------------------------------------------------------------------------------------
+// enumerators: dataset.c:80-201 (host only; the GPU search enumerates tuples itself)
+// -------------------------------------------------------------------------------------
+extern "C" int get_block_stride(size_t block_operations, int order) {
+    return (int) std::ceil(std::pow((double) block_operations, 1.0 / order));
+}
+
+// next multiset of block ids in non-decreasing order, e.g. (0,1,3) -> (0,2,2) when num_blocks = 4
+extern "C" int get_next_block(int num_blocks, int order, int block_coordinates[]) {
+    for (int pos = order - 1; pos >= 0; pos--) {
+        if (block_coordinates[pos] + 1 >= num_blocks) continue;
+        const int v = ++block_coordinates[pos];
+        for (int q = pos + 1; q < order; q++) block_coordinates[q] = v;
+        return 1;
+    }
+    return 0;
+}
+
+extern "C" void get_first_combination_in_block(int order, int init_coordinates[], int block_coordinates[], int stride) {
+    for (int pos = 0; pos < order; pos++) {
+        int v = block_coordinates[pos] * stride;
+        if (pos > 0 && v <= init_coordinates[pos - 1]) v = init_coordinates[pos - 1] + 1;   // same block: consecutive SNPs
+        init_coordinates[pos] = v;
+    }
+}
+
+// Successor of comb inside the block tuple, with the reference's limits (dataset.c:131-171): exact for
+// order 2 (apart from num_variants % stride == 1), incomplete across mixed blocks for order >= 3.
+extern "C" int get_next_combination_in_block(int order, int comb[], int block_coordinates[], int stride, int num_variants) {
+    int pos = order - 1;
+    comb[pos]++;
+    for (;;) {
+        if (pos == 0) break;
+        const int limit = std::min((block_coordinates[pos] + 1) * stride - order + 1 + pos, num_variants);
+        if (comb[pos] < limit) break;
+        pos--;
+        comb[pos]++;
+    }
+    if (comb[0] > (block_coordinates[0] + 1) * stride - 1 || comb[0] >= num_variants) return 0;
+    for (int q = pos + 1; q < order; q++)
+        comb[q] = (block_coordinates[q - 1] == block_coordinates[q]) ? comb[q - 1] + 1 : block_coordinates[q] * stride;
+    const int last = comb[order - 1];
+    if (last > (block_coordinates[order - 1] + 1) * stride - 1 || last >= num_variants) return 0;
+    return 1;
+}
+
+extern "C" uint8_t get_next_genotype_combination(int order, uint8_t comb[]) {
+    // base-3 increment, last SNP fastest; 0 once the first digit overflows
+    for (int pos = order - 1; pos >= 0; pos--) {
+        if (++comb[pos] < 3) return 1;
+        if (pos == 0) return 0;
+        comb[pos] = 0;
+    }
+    return 0;
+}
+
+extern "C" uint8_t **get_genotype_combinations(int order, int *num_combinations) {
+    int n = 1;
+    for (int o = 0; o < order; o++) n *= 3;
+    *num_combinations = n;
+    uint8_t **cells = (uint8_t **) malloc((size_t) n * sizeof(uint8_t *));
+    for (int c = 0; c < n; c++) {
+        cells[c] = (uint8_t *) calloc((size_t) order, 1);
+        int rem = c;
+        for (int pos = order - 1; pos >= 0; pos--) { cells[c][pos] = (uint8_t) (rem % 3); rem /= 3; }
+    }
+    return cells;
+}
+
+// -------------------------------------------------------------------------------------
+// folds: cross_validation.c:4-132
+// -------------------------------------------------------------------------------------
+static int **folds_from_assignment(unsigned A, unsigned U, unsigned k, const int32_t *fos, const uint32_t *sz, unsigned **sizes) {
+    int **folds = (int **) malloc(k * sizeof(int *));
+    unsigned *out = (unsigned *) calloc(3 * (size_t) k, sizeof(unsigned));
+    std::vector<unsigned> fill(k, 0);
+    for (unsigned f = 0; f < k; f++) {
+        out[3 * f] = sz[3 * f]; out[3 * f + 1] = sz[3 * f + 1]; out[3 * f + 2] = sz[3 * f + 2];
+        folds[f] = (int *) malloc(std::max<size_t>(1, sz[3 * f]) * sizeof(int));
+    }
+    for (unsigned s = 0; s < A + U; s++) folds[fos[s]][fill[fos[s]]++] = (int) s;    // ascending ids = the reference's qsort
+    *sizes = out;
+    return folds;
+}
+
+extern "C" int **get_k_folds(unsigned int A, unsigned int U, unsigned int k, unsigned int **sizes) {
+    if (A < k) LOGW("There are less affected samples than folds and they won't be properly distributed\n");
+    if (U < k) LOGW("There are less unaffected samples than folds and they won't be properly distributed\n");
+    std::vector<int32_t> fos((size_t) A + U);
+    std::vector<uint32_t> sz(3 * (size_t) k);
+    const long seed = getenv("HPGV_EPI_SEED") ? env_long("HPGV_EPI_SEED", 0) : clock_seed();
+    hpgv_epi_k_folds((int) A, (int) U, (int) k, seed, fos.data(), sz.data());
+    return folds_from_assignment(A, U, k, fos.data(), sz.data(), sizes);
+}
+
+// byte masks, 1 = training sample, 0 = sample of this fold or padding; controls start at A rounded up to 16
+extern "C" uint8_t *get_k_folds_masks(unsigned int A, unsigned int U, unsigned int k, int **folds, unsigned int *sizes) {
+    const size_t a_pad = 16 * ((A + 15) / 16), u_pad = 16 * ((U + 15) / 16), s_pad = a_pad + u_pad;
+    uint8_t *masks = nullptr;
+    if (posix_memalign((void **) &masks, 16, std::max<size_t>(16, k * s_pad)) != 0) return nullptr;
+    for (unsigned f = 0; f < k; f++) {
+        uint8_t *m = masks + f * s_pad;
+        memset(m, 0, s_pad);
+        memset(m, 1, A);
+        memset(m + a_pad, 1, U);
+        for (unsigned x = 0; x < sizes[3 * f]; x++) {
+            const unsigned s = (unsigned) folds[f][x];
+            m[s < A ? s : a_pad + (s - A)] = 0;
+        }
+    }
+    return masks;
+}
+
+// -------------------------------------------------------------------------------------
+// merge_rankings (epistasis.c:96-153) + report (epistasis_report.c:28-82)
+// -------------------------------------------------------------------------------------
+extern "C" int hpgv_epi_merge_rankings(int order, int num_folds, int rank_size, const void *models_v, enum evaluation_mode mode,
+                                       hpgv_epi_report_row_t *rows, int capacity) {
+    const hpgv_epi_model_t *models = static_cast<const hpgv_epi_model_t *>(models_v);
+    struct Key {
+        int s[3];
+        bool operator<(const Key &o) const { return s[0] != o.s[0] ? s[0] < o.s[0] : (s[1] != o.s[1] ? s[1] < o.s[1] : s[2] < o.s[2]); }
+    };
+    std::map<Key, hpgv_epi_report_row_t> acc;
+    for (int f = 0; f < num_folds; f++) {                     // ascending fold: the risky genotypes of the first fold are kept
+        for (int r = 0; r < rank_size; r++) {
+            const hpgv_epi_model_t &m = models[(size_t) f * rank_size + r];
+            if (m.snp[0] < 0) continue;
+            const Key key{{m.snp[0], m.snp[1], order == 3 ? m.snp[2] : -1}};
+            auto it = acc.find(key);
+            if (it == acc.end()) {
+                hpgv_epi_report_row_t row;
+                memset(&row, 0, sizeof row);
+                row.order = order;
+                row.snp[0] = m.snp[0]; row.snp[1] = m.snp[1]; row.snp[2] = order == 3 ? m.snp[2] : -1;
+                const int cells = order == 2 ? 9 : 27;
+                for (int c = 0; c < cells; c++) {
+                    if (!((m.risky_mask >> c) & 1u)) continue;
+                    int rem = c;
+                    for (int pos = order - 1; pos >= 0; pos--) { row.risky_genotypes[row.num_risky][pos] = (uint8_t) (rem % 3); rem /= 3; }
+                    row.num_risky++;
+                }
+                it = acc.emplace(key, row).first;
+            }
+            it->second.cv_accuracy += m.accuracy;             // NaN propagates like in the reference's sum
+            it->second.cv_count += 1;
+        }
+    }
+    std::vector<hpgv_epi_report_row_t> all;
+    all.reserve(acc.size());
+    for (auto &kv : acc) {
+        kv.second.cv_accuracy /= num_folds;                   // divided by the fold count even when cv_count < folds (epistasis.c:142,148)
+        all.push_back(kv.second);
+    }
+    auto nan_last = [](double a, double b) {                  // descending, NaN after every number
+        if (std::isnan(a)) return false;
+        if (std::isnan(b)) return true;
+        return a > b;
+    };
+    std::stable_sort(all.begin(), all.end(), [&](const hpgv_epi_report_row_t &a, const hpgv_epi_report_row_t &b) {
+        if (mode == CV_C && a.cv_count != b.cv_count) return a.cv_count > b.cv_count;
+        if (a.cv_accuracy != b.cv_accuracy && !(std::isnan(a.cv_accuracy) && std::isnan(b.cv_accuracy))) return nan_last(a.cv_accuracy, b.cv_accuracy);
+        return false;                                         // map order = SNP tuple ascending, kept by the stable sort
+    });
+    const int n = std::min<int>((int) all.size(), capacity);
+    for (int x = 0; x < n; x++) rows[x] = all[x];
+    return n;
+}
+
+extern "C" void hpgv_epi_write_report(int order, int cv_repetition, enum evaluation_mode mode, enum evaluation_subset subset,
+                                      const hpgv_epi_report_row_t *rows, int num_rows, int max_ranking_size, FILE *fd) {
+    fprintf(fd, "#CROSS VALIDATION %d\n", cv_repetition + 1);
+    fprintf(fd, "#COMBINATIONS OF: %d SNPs\n", order);
+    if (mode == CV_C) fprintf(fd, "#EVALUATION MODE: Cross-validation consistency\n");
+    else if (mode == CV_A) fprintf(fd, "#EVALUATION MODE: Cross-validation accuracy\n");
+    if (subset == TRAINING) fprintf(fd, "#EVALUATION PARTITION: Training\n");
+    else if (subset == TESTING) fprintf(fd, "#EVALUATION PARTITION: Testing\n");
+    fprintf(fd, "#POSITION\tSNPs\tGENOTYPES\tCV-C\tCV-A\n");
+    for (int pos = 0; pos < num_rows && pos < max_ranking_size; pos++) {
+        const hpgv_epi_report_row_t &r = rows[pos];
+        fprintf(fd, "%d\t(", pos + 1);
+        for (int s = 0; s < order - 1; s++) fprintf(fd, " %d,", r.snp[s]);
+        fprintf(fd, " %d )\t", r.snp[order - 1]);
+        for (int g = 0; g < r.num_risky; g++) {
+            fprintf(fd, "(%d-", r.risky_genotypes[g][0]);
+            for (int s = 1; s < order - 1; s++) fprintf(fd, "%d, ", r.risky_genotypes[g][s]);
+            fprintf(fd, "%d), ", r.risky_genotypes[g][order - 1]);
+        }
+        fprintf(fd, "%d\t%.3f\n", r.cv_count, r.cv_accuracy);
+    }
+}
+
+// -------------------------------------------------------------------------------------
+// run_epistasis: singlenode/epistasis_runner.c:24-363
+// -------------------------------------------------------------------------------------
+extern "C" int run_epistasis(shared_options_data_t *shared, epistasis_options_data_t *opt) {
+    int num_affected = 0, num_unaffected = 0;
+    size_t num_variants = 0, file_len = 0, genotypes_offset = 0;
+    uint8_t *input_file = epistasis_dataset_load(&num_affected, &num_unaffected, &num_variants, &file_len, &genotypes_offset, opt->dataset_filename);
+    if (!input_file) LOGF("File %s does not exist!\n", opt->dataset_filename);
+    const uint8_t *genotypes = input_file + genotypes_offset;
+    if (file_len < genotypes_offset + num_variants * (size_t) (num_affected + num_unaffected))
+        LOGF("Dataset %s is shorter than its header announces (%zu variants, %d + %d samples)\n", opt->dataset_filename, num_variants, num_affected, num_unaffected);
+
+    const char *outdir = (shared->output_directory && *shared->output_directory) ? shared->output_directory : ".";
+    int ret_code = mkdir(outdir, S_IRWXU | S_IRWXG | S_IROTH | S_IXOTH);
+    if (ret_code != 0 && errno != EEXIST) LOGF("Can't create output directory: %s\n", outdir);
+
+    const int order = opt->order, num_folds = opt->num_folds;
+    const int stride = opt->stride > 0 ? opt->stride : 1;
+    LOGI("Combinations of order %d, %d variants per block\n", order, stride);
+    LOGI("%zu variants, %d blocks per dimension\n", num_variants, (int) ((num_variants + stride - 1) / stride));
+    if (opt->eval_mode == CV_A) LOGI("Using CV-a as ranking criteria\n");
+    else if (opt->eval_mode == CV_C) LOGI("Using CV-c as ranking criteria\n");
+    else LOGF("Rank criteria not specified! Must be 'count' or 'accu'\n");
+    if (order != 2 && order != 3) LOGF("Combinations of order %d are not supported by the GPU engine (2 or 3)\n", order);
+
+    // one engine context per GPU; the combination index space is cut into contiguous ranges
+    int ngpu = (int) env_long("HPGV_EPI_GPUS", 1);
+    int have = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess || have < 1) LOGF("No CUDA device is available: the epistasis engine has no CPU path\n");
+    ngpu = std::max(1, std::min(ngpu, have));
+    std::vector<hpgv_epi_ctx *> ctx((size_t) ngpu, nullptr);
+    for (int g = 0; g < ngpu; g++) {
+        if (hpgv_epi_create(g, &ctx[g]) != HPGV_OK) LOGF("GPU %d: %s\n", g, hpgv_epi_last_error(nullptr));
+        if (hpgv_epi_load_dataset_host(ctx[g], genotypes, (int64_t) num_variants, num_affected, num_unaffected) != HPGV_OK)
+            LOGF("GPU %d: %s\n", g, hpgv_epi_last_error(ctx[g]));
+    }
+    const uint64_t total = hpgv_epi_num_combinations((int64_t) num_variants, order);
+    const int rank = std::max(1, std::min(opt->max_ranking_size, HPGV_MAX_RANK));
+    const size_t nrec = (size_t) num_folds * rank;
+    const bool seeded = getenv("HPGV_EPI_SEED") != nullptr;
+    const long seed0 = env_long("HPGV_EPI_SEED", 0);
+
+    std::vector<int32_t> fos((size_t) num_affected + num_unaffected);
+    std::vector<hpgv_epi_model_t> models(nrec), part(nrec * (size_t) ngpu);
+    std::vector<hpgv_epi_report_row_t> rows(nrec);
+    for (int r = 0; r < opt->num_cv_repetitions; r++) {
+        LOGI("Running cross-validation #%d...\n", r + 1);
+        if (hpgv_epi_k_folds(num_affected, num_unaffected, num_folds, seeded ? seed0 + r : clock_seed(), fos.data(), nullptr) != HPGV_OK)
+            LOGF("Cannot draw %d folds\n", num_folds);
+        for (int g = 0; g < ngpu; g++)
+            if (hpgv_epi_set_folds(ctx[g], num_folds, fos.data()) != HPGV_OK) LOGF("GPU %d: %s\n", g, hpgv_epi_last_error(ctx[g]));
+        if (ngpu == 1) {
+            if (hpgv_epi_search(ctx[0], order, opt->eval_subset, rank, 0, total, models.data()) != HPGV_OK)
+                LOGF("GPU 0: %s\n", hpgv_epi_last_error(ctx[0]));
+        } else {
+            // every GPU searches its range (the launches are asynchronous), then GPU 0 merges the per-range rankings
+            std::vector<hpgv_epi_model_t *> d_part((size_t) ngpu, nullptr);
+            for (int g = 0; g < ngpu; g++) {
+                cudaSetDevice(g);
+                if (cudaMalloc((void **) &d_part[g], nrec * sizeof(hpgv_epi_model_t)) != cudaSuccess) LOGF("GPU %d: out of memory\n", g);
+                const uint64_t lo = total / ngpu * g + std::min<uint64_t>(g, total % ngpu);
+                const uint64_t hi = total / ngpu * (g + 1) + std::min<uint64_t>(g + 1, total % ngpu);
+                if (hpgv_epi_search_device(ctx[g], order, opt->eval_subset, rank, lo, hi, d_part[g]) != HPGV_OK)
+                    LOGF("GPU %d: %s\n", g, hpgv_epi_last_error(ctx[g]));
+            }
+            for (int g = 0; g < ngpu; g++) {
+                cudaSetDevice(g);
+                if (cudaMemcpy(part.data() + nrec * g, d_part[g], nrec * sizeof(hpgv_epi_model_t), cudaMemcpyDeviceToHost) != cudaSuccess)
+                    LOGF("GPU %d: copy of the ranking failed\n", g);
+                cudaFree(d_part[g]);
+                LOGI("Range finished: GPU %d\n", g);
+            }
+            cudaSetDevice(0);
+            hpgv_epi_model_t *d_all = nullptr, *d_out = nullptr;
+            if (cudaMalloc((void **) &d_all, part.size() * sizeof(hpgv_epi_model_t)) != cudaSuccess ||
+                cudaMalloc((void **) &d_out, nrec * sizeof(hpgv_epi_model_t)) != cudaSuccess) LOGF("GPU 0: out of memory\n");
+            cudaMemcpy(d_all, part.data(), part.size() * sizeof(hpgv_epi_model_t), cudaMemcpyHostToDevice);
+            if (hpgv_epi_merge_device(ctx[0], order, opt->eval_subset, ngpu, num_folds, rank, d_all, d_out) != HPGV_OK)
+                LOGF("GPU 0: %s\n", hpgv_epi_last_error(ctx[0]));
+            if (cudaMemcpy(models.data(), d_out, nrec * sizeof(hpgv_epi_model_t), cudaMemcpyDeviceToHost) != cudaSuccess)
+                LOGF("GPU 0: copy of the merged ranking failed\n");
+            cudaFree(d_all);
+            cudaFree(d_out);
+        }
+        const int nrows = hpgv_epi_merge_rankings(order, num_folds, rank, models.data(), opt->eval_mode, rows.data(), (int) rows.size());
+
+        char default_name[32];
+        snprintf(default_name, sizeof default_name, "hpg-variant.cv%d.epi", r + 1);
+        const char *fname = (shared->output_filename && *shared->output_filename) ? shared->output_filename : default_name;
+        const std::string path = std::string(outdir) + "/" + fname;
+        LOGI("Output file will be saved in path %s\n", path.c_str());
+        FILE *fd = fopen(path.c_str(), "w");
+        if (!fd) LOGF("Can't open output file %s\n", path.c_str());
+        hpgv_epi_write_report(order, r, opt->eval_mode, opt->eval_subset, rows.data(), nrows, opt->max_ranking_size, fd);
+        fclose(fd);
+    }
+    for (int g = 0; g < ngpu; g++) hpgv_epi_destroy(ctx[g]);
+    epistasis_dataset_close(input_file, file_len);
+    return ret_code;
+}
+
+// -------------------------------------------------------------------------------------
+// epistasis(): main_epistasis.c:24-118 + epistasis_options_parsing.c:24-182
+// -------------------------------------------------------------------------------------
+namespace {
+
+struct EpiOptions {
+    std::string dataset, outdir, config, eval_subset, eval_mode;
+    bool has_dataset = false, has_order = false, has_subset = false, has_mode = false;
+    long order = 0, stride = 0, num_folds = 0, num_cv = 0, rank = 0, threads = 0, seed = 0, gpus = 0;
+    bool has_seed = false;
+};
+
+// The subset of the libconfig grammar hpg-variant.conf uses: nested groups `name : { ... } ;`, settings
+// `key = value ;` with integer or "string" values, # and // comments.  Collects gwas.epistasis.* settings.
+bool read_epistasis_config(const char *path, std::map<std::string, std::string> &out) {
+    FILE *fp = fopen(path, "r");
+    if (!fp) return false;
+    std::string text;
+    char buf[4096];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, fp)) > 0) text.append(buf, n);
+    fclose(fp);
+    std::vector<std::string> scope;
+    std::string token, pending_name;
+    size_t i = 0;
+    auto skip = [&]() {
+        for (;;) {
+            while (i < text.size() && isspace((unsigned char) text[i])) i++;
+            if (i < text.size() && text[i] == '#') { while (i < text.size() && text[i] != '\n') i++; continue; }
+            if (i + 1 < text.size() && text[i] == '/' && text[i + 1] == '/') { while (i < text.size() && text[i] != '\n') i++; continue; }
+            if (i + 1 < text.size() && text[i] == '/' && text[i + 1] == '*') { i += 2; while (i + 1 < text.size() && !(text[i] == '*' && text[i + 1] == '/')) i++; i += 2; continue; }
+            break;
+        }
+    };
+    while (true) {
+        skip();
+        if (i >= text.size()) break;
+        const char c = text[i];
+        if (isalpha((unsigned char) c) || c == '_' || c == '*') {
+            size_t j = i;
+            while (j < text.size() && (isalnum((unsigned char) text[j]) || text[j] == '_' || text[j] == '-' || text[j] == '*')) j++;
+            pending_name = text.substr(i, j - i);
+            i = j;
+            skip();
+            if (i < text.size() && (text[i] == ':' || text[i] == '=')) {
+                i++;
+                skip();
+                if (i < text.size() && text[i] == '{') { scope.push_back(pending_name); i++; continue; }
+                // scalar value
+                std::string value;
+                if (i < text.size() && text[i] == '"') {
+                    size_t j2 = text.find('"', i + 1);
+                    if (j2 == std::string::npos) return false;
+                    value = text.substr(i + 1, j2 - i - 1);
+                    i = j2 + 1;
+                } else {
+                    size_t j2 = i;
+                    while (j2 < text.size() && text[j2] != ';' && text[j2] != ',' && !isspace((unsigned char) text[j2])) j2++;
+                    value = text.substr(i, j2 - i);
+                    i = j2;
+                }
+                std::string full;
+                for (auto &s : scope) full += s + ".";
+                out[full + pending_name] = value;
+            } else {
+                return false;
+            }
+        } else if (c == '}') {
+            if (scope.empty()) return false;
+            scope.pop_back();
+            i++;
+        } else if (c == ';' || c == ',') {
+            i++;
+        } else {
+            return false;
+        }
+    }
+    return scope.empty();
+}
+
+void usage() {
+    printf("Usage: hpg-var-gwas epi -d|--dataset=<file> [--outdir=<str>] --order=<int> [--num-folds=<int>] [--num-cv-runs=<int>]\n"
+           "                        [--rank-size=<int>] [--eval-subset=<str>] [--eval-mode=<str>] [--stride=<int>] [-c|--config=<file>]\n"
+           "                        [--num-threads=<int>] [--seed=<int>] [--gpus=<int>]\n"
+           "  -d, --dataset=<file>   Binary dataset used as input\n"
+           "  --outdir=<str>         Directory where the output files will be stored\n"
+           "  --order=<int>          Number of SNPs to be combined at the same time\n"
+           "  --num-folds=<int>      Number of folds in a k-fold cross-validation\n"
+           "  --num-cv-runs=<int>    Number of times the k-fold cross-validation process is run\n"
+           "  --rank-size=<int>      Number of best models saved\n"
+           "  --eval-subset=<str>    Whether to used training (default) or testing partitions when evaluating the best models\n"
+           "  --eval-mode=<str>      Whether to rank risky combinations by their CV-C or CV-A (values can be 'count' or 'accu')\n"
+           "  --stride=<int>         Number of SNPs per block partition of the dataset (tiling hint; results do not depend on it)\n"
+           "  -c, --config=<file>    File that contains the parameters for configuring the application\n"
+           "  --num-threads=<int>    Number of threads when a task runs in parallel (host side only)\n"
+           "  --seed=<int>           Draw reproducible folds (repetition r uses seed + r); default: microsecond clock\n"
+           "  --gpus=<int>           Number of GPUs of this box to shard the combination space over (default 1)\n");
+}
+
+}  // namespace
+
+extern "C" int epistasis(int argc, char *argv[], const char *configuration_file) {
+    if (argc == 1 || !strcmp(argv[1], "-h") || !strcmp(argv[1], "--help")) {
+        usage();
+        return 0;
+    }
+    EpiOptions o;
+    // Step 1: configuration file (keys gwas.epistasis.*, epistasis_options_parsing.c:39-89)
+    if (configuration_file) {
+        std::map<std::string, std::string> cfg;
+        if (!read_epistasis_config(configuration_file, cfg)) {
+            LOGE("Configuration file error: cannot parse %s\n", configuration_file);
+            LOGE("Configuration file read with errors\n");
+            return 2;   /* CANT_READ_CONFIG_FILE */
+        }
+        auto num = [&](const char *key, long &dst, const char *what) {
+            auto it = cfg.find(std::string("gwas.epistasis.") + key);
+            if (it == cfg.end()) LOGW("%s not found in configuration file, must be set via command-line\n", what);
+            else dst = strtol(it->second.c_str(), nullptr, 10);
+        };
+        num("num-threads", o.threads, "Number of threads");
+        num("stride", o.stride, "Number of SNPs per block partition");
+        num("num-folds", o.num_folds, "Number of folds per k-fold cross-validation");
+        num("num-cv-repetitions", o.num_cv, "Number of cross-validation repetitions");
+        num("max-ranking-size", o.rank, "Maximum number of best models recorded");
+        auto it = cfg.find("gwas.epistasis.evaluation-subset");
+        if (it == cfg.end()) LOGW("Evaluation subset not found in configuration file, must be set via command-line\n");
+        else { o.eval_subset = it->second; o.has_subset = true; }
+        it = cfg.find("gwas.epistasis.evaluation-mode");
+        if (it == cfg.end()) LOGW("Evaluation mode not found in configuration file, must be set via command-line\n");
+        else { o.eval_mode = it->second; o.has_mode = true; }
+    } else {
+        // no configuration file at all: the defaults the reference ships in etc/hpg-variant/hpg-variant.conf:36-45
+        o.stride = 100; o.num_folds = 10; o.num_cv = 10; o.rank = 50; o.threads = 4;
+        o.eval_subset = "training"; o.has_subset = true;
+        o.eval_mode = "count"; o.has_mode = true;
+    }
+    // Step 2: command line overrides the configuration file
+    int errors = 0;
+    for (int a = 1; a < argc; a++) {
+        std::string arg = argv[a], name, value;
+        bool has_value = false;
+        if (arg.rfind("--", 0) == 0) {
+            const size_t eq = arg.find('=');
+            name = arg.substr(2, eq == std::string::npos ? std::string::npos : eq - 2);
+            if (eq != std::string::npos) { value = arg.substr(eq + 1); has_value = true; }
+        } else if (arg == "-d" || arg == "-c") {
+            name = arg == "-d" ? "dataset" : "config";
+        } else if (arg.rfind("-d", 0) == 0 || arg.rfind("-c", 0) == 0) {
+            name = arg[1] == 'd' ? "dataset" : "config";
+            value = arg.substr(2); has_value = true;
+        } else {
+            printf("hpg-var-gwas: unexpected argument \"%s\"\n", arg.c_str());
+            errors++;
+            continue;
+        }
+        if (!has_value) {
+            if (a + 1 >= argc) { printf("hpg-var-gwas: option \"%s\" requires an argument\n", arg.c_str()); errors++; continue; }
+            value = argv[++a];
+        }
+        char *end = nullptr;
+        auto as_long = [&](long &dst) {
+            dst = strtol(value.c_str(), &end, 10);
+            if (end == value.c_str() || *end) { printf("hpg-var-gwas: invalid argument \"%s\" to option --%s\n", value.c_str(), name.c_str()); errors++; }
+        };
+        if (name == "dataset") { o.dataset = value; o.has_dataset = true; }
+        else if (name == "outdir") o.outdir = value;
+        else if (name == "config") o.config = value;
+        else if (name == "order") { as_long(o.order); o.has_order = true; }
+        else if (name == "num-folds") as_long(o.num_folds);
+        else if (name == "num-cv-runs") as_long(o.num_cv);
+        else if (name == "rank-size") as_long(o.rank);
+        else if (name == "stride") as_long(o.stride);
+        else if (name == "num-threads") as_long(o.threads);
+        else if (name == "eval-subset") { o.eval_subset = value; o.has_subset = true; }
+        else if (name == "eval-mode") { o.eval_mode = value; o.has_mode = true; }
+        else if (name == "seed") { as_long(o.seed); o.has_seed = true; }
+        else if (name == "gpus") as_long(o.gpus);
+        else { printf("hpg-var-gwas: invalid option \"%s\"\n", arg.c_str()); errors++; }
+    }
+    (void) errors;   // like the reference, parse errors are printed and verification decides (epistasis_options_parsing.c:105-112)
+
+    // Step 3: verification, with the reference's messages and codes (epistasis_options_parsing.c:143-182)
+    if (!o.has_dataset) { LOGE("Please specify the dataset file.\n"); return EPISTASIS_DATASET_NOT_SPECIFIED; }
+    if (!o.has_order || o.order == 0) { LOGE("Please specify the number of SNPs to be combined at the same time.\n"); return EPISTASIS_ORDER_NOT_SPECIFIED; }
+    if (o.num_folds == 0) { LOGE("Please specify the number of folds in a k-fold cross-validation.\n"); return EPISTASIS_FOLDS_NOT_SPECIFIED; }
+    if (o.num_cv == 0) { LOGE("Please specify the times the cross-validation will be run.\n"); return EPISTASIS_CV_RUNS_NOT_SPECIFIED; }
+    if (!o.has_subset || (o.eval_subset != "training" && o.eval_subset != "testing")) {
+        LOGE("Please specify the dataset partition for evaluating the best models (training/testing).\n");
+        return EPISTASIS_EVAL_SUBSET_NOT_SPECIFIED;
+    }
+    if (o.stride == 0) { LOGE("Please specify the number of SNPs per block partition of the dataset.\n"); return EPISTASIS_STRIDE_NOT_SPECIFIED; }
+
+    // Step 4: option structures (main_epistasis.c:134-146: anything but "testing" is TRAINING, anything but "count" is CV_A)
+    shared_options_data_t shared;
+    memset(&shared, 0, sizeof shared);
+    std::string outdir = o.outdir;
+    shared.output_directory = outdir.empty() ? nullptr : &outdir[0];
+    shared.num_threads = (int) o.threads;
+    epistasis_options_data_t opt;
+    memset(&opt, 0, sizeof opt);
+    std::string dataset = o.dataset;
+    opt.dataset_filename = &dataset[0];
+    opt.order = (int) o.order;
+    opt.stride = (int) o.stride;
+    opt.num_folds = (int) o.num_folds;
+    opt.num_cv_repetitions = (int) o.num_cv;
+    opt.max_ranking_size = (int) (o.rank > 0 ? o.rank : 50);
+    opt.eval_subset = o.eval_subset == "testing" ? TESTING : TRAINING;
+    opt.eval_mode = (o.has_mode && o.eval_mode == "count") ? CV_C : CV_A;
+    if (o.has_seed) setenv("HPGV_EPI_SEED", std::to_string(o.seed).c_str(), 1);
+    if (o.gpus > 0) setenv("HPGV_EPI_GPUS", std::to_string(o.gpus).c_str(), 1);
+
+    // Step 5
+    run_epistasis(&shared, &opt);
+    return 0;
+}
+
+extern "C" void hpgv_epi_host_open_log(const char *path) {
+    if (g_log_file) fclose(g_log_file);
+    g_log_file = path ? fopen(path, "w") : nullptr;
+}

@@ -387,6 +387,18 @@ __device__ __forceinline__ void single_block3(const uint32_t *irow, const uint32
     }
 }
 
+// The counting phase of a tuple is bound by the XU pipe (POPC), its epilogue by the ALU.  Warps of one SM sub-partition
+// that run in lockstep leave each pipe idle half of the time; delaying the upper half of the warps once, by about half
+// the counting time of a unit, lets one half count while the other half evaluates.  (The stage hand-off tolerates a
+// drift of one step, so the offset persists.)
+__device__ __forceinline__ void stagger_late_warps(int warp, int nwarps, int unit_cycles_per_warp) {
+    if (nwarps >= 8 && warp >= nwarps / 2) {
+        const long long wait = (long long) unit_cycles_per_warp * (nwarps / 4) / 2;
+        const long long t0 = clock64();
+        while (clock64() - t0 < wait) {}
+    }
+}
+
 // common prologue: barriers, control block, counters, block descriptors
 template <bool SINGLE>
 __device__ __forceinline__ void search_init(SearchCtl *ctl, const SearchArgs &a, uint32_t *cnt_base, size_t cnt_words, uint16_t *desc) {
@@ -497,6 +509,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
         const int4 meta = ctl->meta[s % 3];
         if (meta.x < 0) break;
         const int ch = meta.x, i0 = meta.y, j0 = meta.z;
+        if (s == 0) stagger_late_warps(warp, TI, nblocks * 9 * (BW == 4 ? 24 : 34));
         if (ch == 0 && warp == 0 && lane < ctl->fl.F) atomicMax(&ctl->thr[lane], __ldcg(a.gthr + lane));
 
         const uint32_t *sbase = reinterpret_cast<const uint32_t *>(smem_raw + sm.stage0 + (size_t) st * sm.stage_bytes);
@@ -643,6 +656,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3_kernel(const Search
         const int4 meta = ctl->meta[s % 3];
         if (meta.x < 0) break;
         const int ch = meta.x, i = meta.y, j0 = meta.z, k0 = meta.w;
+        if (s == 0) stagger_late_warps(warp, TJ, nblocks * 27 * (BW == 4 ? 24 : 34));
         if (ch == 0 && warp == 0 && lane < ctl->fl.F) atomicMax(&ctl->thr[lane], __ldcg(a.gthr + lane));
 
         const uint32_t *sbase = reinterpret_cast<const uint32_t *>(smem_raw + sm.stage0 + (size_t) st * sm.stage_bytes);

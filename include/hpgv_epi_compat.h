@@ -80,7 +80,8 @@ int run_epistasis(shared_options_data_t *shared_options_data, epistasis_options_
 /* src/gwas/main_gwas.h:46 (src/gwas/epistasis/main_epistasis.c:24-118): config file, then the command
  * line (-d/--dataset, --order, --stride, --num-folds, --num-cv-runs, --rank-size, --eval-subset,
  * --eval-mode, --outdir, --config, --num-threads; plus --seed and --gpus), verification with the
- * reference's error codes, then run_epistasis.  Returns 0 like the reference (it ignores run_epistasis's code). */
+ * reference's error codes, then run_epistasis.  Returns 0 like the reference (it ignores run_epistasis's code).
+ * configuration_file == NULL applies the defaults the reference ships in etc/hpg-variant/hpg-variant.conf:36-45. */
 int epistasis(int argc, char *argv[], const char *configuration_file);
 
 /* src/gwas/epistasis/dataset.h:53-55 (dataset.c:54-72): mmap of the whole file.  Accepts the current
@@ -124,6 +125,9 @@ int hpgv_epi_merge_rankings(int order, int num_folds, int rank_size, const void 
 /* epistasis_report (epistasis_report.c:28-82), same text format, at most max_ranking_size rows */
 void hpgv_epi_write_report(int order, int cv_repetition, enum evaluation_mode mode, enum evaluation_subset subset,
                            const hpgv_epi_report_row_t *rows, int num_rows, int max_ranking_size, FILE *fd);
+
+/* The reference logs to stdout/stderr and to hpg-var-gwas.log (main_gwas.c:32).  Opens (path) or closes (NULL) the log file. */
+void hpgv_epi_host_open_log(const char *path);
 
 #ifdef __cplusplus
 }

@@ -1,7 +1,7 @@
 #!/bin/bash
 # quick iteration: GPU parity tests + short benches (no CPU baseline)
 mkdir -p gpurun_out
-timeout 500 python -m pytest tests -m gpu -x -q --timeout 60 2>&1 | tail -8 | tee gpurun_out/pytest_gpu.txt
+timeout 700 python -m pytest tests -m gpu -x -q --timeout 120 2>&1 | tail -8 | tee gpurun_out/pytest_gpu.txt
 for WL in ${@:-c2}; do
   timeout 600 python bench.py --workload $WL --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$WL.json 2> gpurun_out/bench_$WL.err; echo "bench $WL rc=$?"
   tail -2 gpurun_out/bench_$WL.err
