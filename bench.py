@@ -233,7 +233,7 @@ def main():
 
     import torch
     import hpg_variant_b200 as h
-    from hpg_variant_b200 import synth
+    from hpg_variant_b200 import sharding, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -251,7 +251,7 @@ def main():
     nv, A, U, order, F = w["nv"], w["A"], w["U"], w["order"], w["folds"]
     S = A + U
     total = h.num_combinations(nv, order)
-    first, last = total * rank // world, total * (rank + 1) // world
+    first, last = sharding.shard_range(total, rank, world)
 
     g_pinned = torch.empty((nv, S), dtype=torch.uint8).pin_memory()
     g = g_pinned.numpy()
@@ -264,19 +264,15 @@ def main():
     d_raw = g_pinned.cuda(non_blocking=False)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     rec_bytes = F * RANK_SIZE * 40
-    d_local = torch.zeros(rec_bytes, dtype=torch.uint8, device="cuda")
-    d_all = torch.zeros(world * rec_bytes, dtype=torch.uint8, device="cuda")
-    d_final = torch.zeros(rec_bytes, dtype=torch.uint8, device="cuda")
+    shard = sharding.ShardedSearch(eng, dist, rank, world, F, RANK_SIZE, "cuda")
+    d_local, d_all, d_final = shard.d_local, shard.d_all, shard.d_final
     h_out = np.zeros((F, RANK_SIZE), h.MODEL_DTYPE)
 
     def step_device():
         """pack + search (+ all-gather + merge) with the genotype bytes resident in HBM"""
         eng.load_dataset_device(d_raw.data_ptr(), nv, A, U)
         eng.set_folds(F, fos)
-        eng.search_device(order, h.SUBSET_TRAINING, RANK_SIZE, first, last, d_local.data_ptr())
-        if world > 1:
-            dist.all_gather_into_tensor(d_all, d_local)
-            eng.merge_device(order, h.SUBSET_TRAINING, world, RANK_SIZE, d_all.data_ptr(), d_final.data_ptr())
+        shard.run(order, h.SUBSET_TRAINING, total)     # search [-> all-gather -> merge]
 
     def barrier():
         torch.cuda.synchronize()
