@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhpgv_epi.so")
+# HPGV_EPI_LIB: development override (A/B runs of kernel variants built side by side); never a CPU path
+LIB_PATH = os.environ.get("HPGV_EPI_LIB") or os.path.join(HERE, "libhpgv_epi.so")
 
 MODEL_DTYPE = np.dtype([("accuracy", "<f8"), ("snp", "<i4", (3,)), ("risky_mask", "<u4"), ("conf", "<u4", (4,))])
 assert MODEL_DTYPE.itemsize == 40

@@ -274,8 +274,10 @@ extern "C" int hpgv_epi_set_folds(hpgv_epi_ctx *ctx, int F, const int32_t *fold_
         seg_size[2 * f + (s < A ? 0 : 1)]++;
     }
     int max_seg = 0;
+    fl.eqfolds = 1;
     for (int f = 0; f < F; f++) {
         fl.a_in[f] = seg_size[2 * f]; fl.u_in[f] = seg_size[2 * f + 1];
+        if (fl.a_in[f] != fl.u_in[f]) fl.eqfolds = 0;
         max_seg = std::max(max_seg, std::max(fl.a_in[f], fl.u_in[f]));
     }
     if (max_seg > 65535) FAIL(HPGV_E_UNSUPPORTED, "more than 65535 samples of one class in one fold");
@@ -284,10 +286,19 @@ extern "C" int hpgv_epi_set_folds(hpgv_epi_ctx *ctx, int F, const int32_t *fold_
     fl.single = max_seg <= 255;
     fl.bw = max_seg <= 128 ? 4 : 8;
     const int bits_per_block = 32 * fl.bw;
+    // 8-word blocks: when 224 sample bits per block need no more blocks than 256 do, the last word of every block stays
+    // empty and the search kernels compress 7 words into 3 POPCs instead of 8 into 4
+    fl.w7 = 0;
+    if (fl.bw == 8) {
+        int nb7 = 0, nb8 = 0;
+        for (int s = 0; s < 2 * F; s++) { nb7 += std::max(1, (seg_size[s] + 223) / 224); nb8 += std::max(1, (seg_size[s] + 255) / 256); }
+        fl.w7 = (nb7 == nb8) ? 1 : 0;
+    }
+    const int used_bits = fl.w7 ? 224 : bits_per_block;
     std::vector<int> seg_blocks(2 * F), seg_first(2 * F);
     int nb = 0;
     for (int s = 0; s < 2 * F; s++) {
-        seg_blocks[s] = fl.single ? 1 : std::max(1, (seg_size[s] + bits_per_block - 1) / bits_per_block);
+        seg_blocks[s] = fl.single ? 1 : std::max(1, (seg_size[s] + used_bits - 1) / used_bits);
         seg_first[s] = nb;
         nb += seg_blocks[s];
     }
@@ -318,7 +329,8 @@ extern "C" int hpgv_epi_set_folds(hpgv_epi_ctx *ctx, int F, const int32_t *fold_
         std::vector<int> fill(2 * F, 0);
         for (int s = 0; s < S; s++) {       // ascending dataset column inside each segment
             const int seg = 2 * fold_of_sample[s] + (s < A ? 0 : 1);
-            ctx->perm[(size_t) seg_first[seg] * bits_per_block + fill[seg]++] = s;
+            const int p = fill[seg]++;
+            ctx->perm[(size_t) (seg_first[seg] + p / used_bits) * bits_per_block + p % used_bits] = s;
         }
     }
     ctx->fl = fl;
@@ -580,6 +592,10 @@ static int do_search(hpgv_epi_ctx *ctx, int order, int eval_subset, int rank, ui
     do {                                                                                             \
         if (fl.bw == 4) grid = balanced ? launch_search(ctx, KERNEL<4, true, true>, shape, args, F, rank)    \
                                         : launch_search(ctx, KERNEL<4, true, false>, shape, args, F, rank);  \
+        else if (fl.w7 && fl.single) grid = balanced ? launch_search(ctx, KERNEL<7, true, true>, shape, args, F, rank)    \
+                                                     : launch_search(ctx, KERNEL<7, true, false>, shape, args, F, rank);  \
+        else if (fl.w7) grid = balanced ? launch_search(ctx, KERNEL<7, false, true>, shape, args, F, rank)      \
+                                        : launch_search(ctx, KERNEL<7, false, false>, shape, args, F, rank);    \
         else if (fl.single) grid = balanced ? launch_search(ctx, KERNEL<8, true, true>, shape, args, F, rank)    \
                                             : launch_search(ctx, KERNEL<8, true, false>, shape, args, F, rank);  \
         else grid = balanced ? launch_search(ctx, KERNEL<8, false, true>, shape, args, F, rank)      \

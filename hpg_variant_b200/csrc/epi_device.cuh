@@ -41,7 +41,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {}
+    if (mbar_try_wait(bar, parity)) return;
+    while (!mbar_try_wait(bar, parity)) __nanosleep(32);     // leave the issue slots to the warps that still count
 }
 // global -> shared, completion signalled on an mbarrier (complete_tx::bytes)
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
@@ -53,8 +54,12 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 // ----------------------------------------------------------------------------
 // bit counting: AND the planes, compress with carry-save adders (LOP3 on the
 // ALU pipe), POPC (XU pipe) the compressed words, weight and accumulate with
-// IMAD (FMA pipe).  Per block of BW words: BW=4 -> 3 POPC, BW=8 -> 4 POPC.
+// IMAD (FMA pipe).  Per block of BW words: BW=4 -> 3 POPC, BW=8 -> 4 POPC,
+// BW=7 (8-word slots, last word empty) -> 3 POPC.
 // ----------------------------------------------------------------------------
+// words a block occupies in a row (BW = 7 counts 7 words of an 8-word slot)
+__host__ __device__ constexpr int slot_words(int BW) { return BW == 7 ? 8 : BW; }
+
 __device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t d;
     asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
@@ -88,8 +93,18 @@ __device__ __forceinline__ uint32_t count_words_acc(const uint32_t (&x)[BW], uin
         acc = mad_const<K>(__popc(x[3]), acc);
         acc = mad_const<2 * K>(__popc(twos), acc);
         return acc;
+    } else if constexpr (BW == 7) {
+        // 8-word slots whose last word is never populated (segments of <= 224 samples): 7 words -> 3 POPC
+        const uint32_t s1 = xor3(x[0], x[1], x[2]), c1 = maj3(x[0], x[1], x[2]);
+        const uint32_t s2 = xor3(x[3], x[4], x[5]), c2 = maj3(x[3], x[4], x[5]);
+        const uint32_t s3 = xor3(s1, s2, x[6]),     c3 = maj3(s1, s2, x[6]);
+        const uint32_t t  = xor3(c1, c2, c3),       f  = maj3(c1, c2, c3);
+        acc = mad_const<K>(__popc(s3), acc);
+        acc = mad_const<2 * K>(__popc(t), acc);
+        acc = mad_const<4 * K>(__popc(f), acc);
+        return acc;
     } else {
-        static_assert(BW == 8, "block width must be 4 or 8 words");
+        static_assert(BW == 8, "block width must be 4, 7 (of 8) or 8 words");
         const uint32_t s1 = xor3(x[0], x[1], x[2]), c1 = maj3(x[0], x[1], x[2]);
         const uint32_t s2 = xor3(x[3], x[4], x[5]), c2 = maj3(x[3], x[4], x[5]);
         const uint32_t s3 = xor3(s1, s2, x[6]),     c3 = maj3(s1, s2, x[6]);
@@ -121,9 +136,10 @@ __device__ __forceinline__ uint32_t cell_count3_acc(const uint32_t (&a)[BW], con
 template <int BW>
 __device__ __forceinline__ void load_plane(const uint32_t *p, uint32_t (&v)[BW]) {
 #pragma unroll
-    for (int q = 0; q < BW / 4; q++) {
+    for (int q = 0; q < slot_words(BW) / 4; q++) {
         const uint4 t = *reinterpret_cast<const uint4 *>(p + 4 * q);
-        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z;
+        if (4 * q + 3 < BW) v[4 * q + 3] = t.w;
     }
 }
 

@@ -80,12 +80,16 @@ struct __align__(16) SearchCtl {
     uint64_t empty[2];             // per stage: every warp is done reading it
     int4 meta[3];                  // step descriptors: x = chunk (-1: no more work), y/z/w = tile origins
     long long thr[kMaxFolds];      // score a candidate must reach to be offered to the list
+    int tq[kMaxFolds];             // the same bound on sum_c max(0, trA - trU) (balanced pre-filter): ceil(thr / n_f)
     int lock[kMaxFolds];
     int cnt[kMaxFolds];
     FoldLayout fl;
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// words between the counter slices of two consecutive threads: cells x counter words, made odd (bank-conflict free)
+__host__ __device__ inline int counter_stride(int ncells, int nwc) { return (ncells * nwc) | 1; }
 
 // dynamic shared memory map of the search kernels (the host uses the same function to size the launch)
 struct SmemMap {
@@ -97,10 +101,18 @@ __host__ __device__ inline SmemMap search_smem_map(const FoldLayout &fl, int row
     m.stage_bytes = align_up((size_t) rows * fl.row_words * 4, 128);
     m.counters = m.stage0 + 2 * m.stage_bytes;
     const int nwc = fl.single ? fl.nblocks / 4 : fl.F;
-    m.desc = m.counters + (size_t) ncells * nwc * nthreads * 4;
+    m.desc = m.counters + (size_t) counter_stride(ncells, nwc) * nthreads * 4;
     m.lists = align_up(m.desc + (fl.single ? 0 : (size_t) fl.nblocks * 2), 16);
     m.total = m.lists + (lists_in_smem ? (size_t) fl.F * rank * sizeof(Cand) : 0);
     return m;
+}
+
+// smallest t with t * n >= thr: the pre-filter's bound for a fold whose training part holds n cases and n controls
+__device__ __forceinline__ int thr_quotient(long long thr, int n) {
+    if (thr == LLONG_MIN || n <= 0) return INT_MIN;
+    long long q = thr / n;
+    if (thr % n > 0) q++;
+    return q > INT_MAX ? INT_MAX : (q < INT_MIN ? INT_MIN : (int) q);
 }
 
 // ---- top-N list maintenance (one list per CTA and fold) ------------------------
@@ -158,6 +170,7 @@ __device__ __forceinline__ void warp_offer(SearchCtl *ctl, const SearchArgs &a, 
             const int nneg = a.training ? fl.U - fl.u_in[f] : fl.u_in[f];
             const long long sc = (npos == 0 || nneg == 0) ? LLONG_MIN : ba_score(root.tp, root.fp, npos, nneg);
             atomicMax(&ctl->thr[f], sc);
+            atomicMax(&ctl->tq[f], thr_quotient(sc, npos));
             atomicMax(a.gthr + f, sc);
         }
         __threadfence_block();
@@ -192,7 +205,7 @@ __device__ __forceinline__ void offer_fold(SearchCtl *ctl, const SearchArgs &a, 
 }
 
 // ---- per-tuple epilogue ---------------------------------------------------------
-// cnts: this thread's private counters, word (c, k) at cnts[(c * nwc + k) * nthreads].
+// cnts: this thread's private counters, word (c, k) at cnts[k * NCELLS + c].
 // U8  (single-block segments): word k of cell c = bytes (A_2k, A_2k+1, U_2k, U_2k+1) of folds 2k and 2k+1
 // !U8 (multi-block segments) : word f of cell c = A_f | U_f << 16
 //
@@ -209,7 +222,7 @@ __device__ __forceinline__ void epilogue_general(SearchCtl *ctl, const SearchArg
     for (int k = 0; k < nwc; k++) {
 #pragma unroll
         for (int c = 0; c < NCELLS; c++) {
-            const uint32_t w = cnts[(c * nwc + k) * nthreads];
+            const uint32_t w = cnts[k * NCELLS + c];
             if constexpr (U8) {
                 totA[c] = __dp4a(w, 0x00000101u, (uint32_t) totA[c]);
                 totU[c] = __dp4a(w, 0x01010000u, (uint32_t) totU[c]);
@@ -225,7 +238,7 @@ __device__ __forceinline__ void epilogue_general(SearchCtl *ctl, const SearchArg
         const int k = U8 ? (f >> 1) : f;
 #pragma unroll
         for (int c = 0; c < NCELLS; c++) {
-            const uint32_t w = cnts[(c * nwc + k) * nthreads];
+            const uint32_t w = cnts[k * NCELLS + c];
             int inA, inU;
             if constexpr (U8) { inA = (int) ((w >> ((f & 1) * 8)) & 0xffu); inU = (int) ((w >> (16 + (f & 1) * 8)) & 0xffu); }
             else { inA = (int) (w & 0xffffu); inU = (int) (w >> 16); }
@@ -297,6 +310,57 @@ __device__ __forceinline__ void balanced_fold(SearchCtl *ctl, const SearchArgs &
     offer_fold(ctl, a, lists, f, valid, score, degenerate, npos, nneg, si, sj, sk, mask, tp, fp, lane);
 }
 
+// d = c + sum over the four bytes of a (unsigned) times the bytes of b (signed)
+__device__ __forceinline__ int dp4a_us(uint32_t a8x4, uint32_t b8x4, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a8x4), "r"(b8x4), "r"(c));
+    return d;
+}
+
+// Pre-filter of the balanced TRAINING epilogue when every fold has as many cases as controls (the layout of
+// get_k_folds on a balanced data set): the training part of fold f holds n_f cases and n_f controls, a cell is high
+// risk iff trA >= trU (and not empty), so
+//     score_f = TP * n_f - FP * n_f = n_f * sum_c max(0, trA_c - trU_c) = n_f * sum_c max(0, D_c - d_cf)
+// with D_c = totA_c - totU_c and d_cf = inA_cf - inU_cf: one IDP (dot product with +-1 bytes) and one VIMNMX.RELU per
+// cell and fold, no unpacking, no risk mask.  Returns whether any fold of this thread's tuple reaches the fold's bound
+// ctl->tq; only then is the exact epilogue (masks, TP/FP, BA, list offer) run.  A stale (lower) bound only costs time.
+template <int NCELLS, bool U8>
+__device__ __forceinline__ bool balanced_prefilter(const SearchCtl *ctl, const uint32_t *cnts, int nwc, int nthreads) {
+    int D[NCELLS];
+#pragma unroll
+    for (int c = 0; c < NCELLS; c++) D[c] = 0;
+    for (int k = 0; k < nwc; k++) {
+#pragma unroll
+        for (int c = 0; c < NCELLS; c++) {
+            const uint32_t w = cnts[k * NCELLS + c];
+            D[c] = U8 ? dp4a_us(w, 0xFFFF0101u, D[c]) : dp2a_lo_us(w, 0x0000FF01u, D[c]);
+        }
+    }
+    const volatile int *tq = ctl->tq;
+    bool pass = false;
+    for (int k = 0; k < nwc; k++) {
+        if constexpr (U8) {                                   // w = bytes (A_2k, A_2k+1, U_2k, U_2k+1)
+            int t0 = 0, t1 = 0;
+#pragma unroll
+            for (int c = 0; c < NCELLS; c++) {
+                const uint32_t w = cnts[k * NCELLS + c];
+                t0 += max(dp4a_us(w, 0x000100FFu, D[c]), 0);
+                t1 += max(dp4a_us(w, 0x0100FF00u, D[c]), 0);
+            }
+            pass |= (t0 >= tq[2 * k]) | (t1 >= tq[2 * k + 1]);
+        } else {                                              // w = A_k | U_k << 16
+            int t = 0;
+#pragma unroll
+            for (int c = 0; c < NCELLS; c++) {
+                const uint32_t w = cnts[k * NCELLS + c];
+                t += max(dp2a_lo_us(w, 0x000001FFu, D[c]), 0);
+            }
+            pass |= t >= tq[k];
+        }
+    }
+    return pass;
+}
+
 // Fast version for balanced data sets (A == U <= 65535): every count pair travels as
 // one register (cases | controls << 16); r = A/U = 1 makes the float32 rule exact,
 // risky <=> trA >= trU and trA > 0 (see high_risk()).
@@ -304,6 +368,12 @@ template <int NCELLS, bool U8, bool TRAINING>
 __device__ __forceinline__ void epilogue_balanced_t(SearchCtl *ctl, const SearchArgs &a, Cand *lists, const uint32_t *cnts, int nwc,
                                                     int nthreads, bool valid, int si, int sj, int sk, int lane) {
     const int nfolds = ctl->fl.F;
+    if constexpr (TRAINING) {
+        if (ctl->fl.eqfolds) {
+            const bool pass = balanced_prefilter<NCELLS, U8>(ctl, cnts, nwc, nthreads);
+            if (!__any_sync(0xffffffffu, pass && valid)) return;
+        }
+    }
     uint32_t tot[NCELLS];                     // total cases | total controls << 16
     if constexpr (U8) {
         uint32_t tA[NCELLS], tU[NCELLS];
@@ -312,7 +382,7 @@ __device__ __forceinline__ void epilogue_balanced_t(SearchCtl *ctl, const Search
         for (int k = 0; k < nwc; k++) {
 #pragma unroll
             for (int c = 0; c < NCELLS; c++) {
-                const uint32_t w = cnts[(c * nwc + k) * nthreads];
+                const uint32_t w = cnts[k * NCELLS + c];
                 tA[c] = __dp4a(w, 0x00000101u, tA[c]);
                 tU[c] = __dp4a(w, 0x01010000u, tU[c]);
             }
@@ -322,7 +392,7 @@ __device__ __forceinline__ void epilogue_balanced_t(SearchCtl *ctl, const Search
         for (int k = 0; 2 * k < nfolds; k++) {
             uint32_t w[NCELLS];
 #pragma unroll
-            for (int c = 0; c < NCELLS; c++) w[c] = cnts[(c * nwc + k) * nthreads];
+            for (int c = 0; c < NCELLS; c++) w[c] = cnts[k * NCELLS + c];
             balanced_fold<NCELLS, TRAINING>(ctl, a, lists, tot, 2 * k, [&](int c) { return __byte_perm(w[c], 0u, 0x4240); }, valid, si, sj, sk, lane);
             if (2 * k + 1 < nfolds)
                 balanced_fold<NCELLS, TRAINING>(ctl, a, lists, tot, 2 * k + 1, [&](int c) { return __byte_perm(w[c], 0u, 0x4341); }, valid, si, sj, sk, lane);
@@ -332,10 +402,10 @@ __device__ __forceinline__ void epilogue_balanced_t(SearchCtl *ctl, const Search
         for (int c = 0; c < NCELLS; c++) tot[c] = 0;
         for (int k = 0; k < nwc; k++) {
 #pragma unroll
-            for (int c = 0; c < NCELLS; c++) tot[c] += cnts[(c * nwc + k) * nthreads];
+            for (int c = 0; c < NCELLS; c++) tot[c] += cnts[k * NCELLS + c];
         }
         for (int f = 0; f < nfolds; f++)
-            balanced_fold<NCELLS, TRAINING>(ctl, a, lists, tot, f, [&](int c) { return cnts[(c * nwc + f) * nthreads]; }, valid, si, sj, sk, lane);
+            balanced_fold<NCELLS, TRAINING>(ctl, a, lists, tot, f, [&](int c) { return cnts[f * NCELLS + c]; }, valid, si, sj, sk, lane);
     }
 }
 template <int NCELLS, bool U8>
@@ -352,32 +422,32 @@ __host__ __device__ constexpr uint32_t group_shift(int q) { return q == 0 ? 0u :
 // block Q (0..3) of a four-block group, single-block segments: the nine (27) cell counts go to byte group_shift(Q) of pk[]
 template <int BW, int Q>
 __device__ __forceinline__ void single_block2(const uint32_t *irow, const uint32_t *jrow, uint32_t (&pk)[9]) {
-    constexpr int off = Q * 3 * BW;
+    constexpr int SW = slot_words(BW), off = Q * 3 * SW;
     uint32_t pj[3][BW];
 #pragma unroll
-    for (int g = 0; g < 3; g++) load_plane<BW>(jrow + off + g * BW, pj[g]);
+    for (int g = 0; g < 3; g++) load_plane<BW>(jrow + off + g * SW, pj[g]);
 #pragma unroll
     for (int ga = 0; ga < 3; ga++) {
         uint32_t pi[BW];
-        load_plane<BW>(irow + off + ga * BW, pi);
+        load_plane<BW>(irow + off + ga * SW, pi);
 #pragma unroll
         for (int gb = 0; gb < 3; gb++) pk[ga * 3 + gb] = cell_count2_acc<BW, (1u << group_shift(Q))>(pi, pj[gb], pk[ga * 3 + gb]);
     }
 }
 template <int BW, int Q>
 __device__ __forceinline__ void single_block3(const uint32_t *irow, const uint32_t *jrow, const uint32_t *krow, uint32_t (&pk)[27]) {
-    constexpr int off = Q * 3 * BW;
+    constexpr int SW = slot_words(BW), off = Q * 3 * SW;
     uint32_t pl[3][BW];
 #pragma unroll
-    for (int g = 0; g < 3; g++) load_plane<BW>(krow + off + g * BW, pl[g]);
+    for (int g = 0; g < 3; g++) load_plane<BW>(krow + off + g * SW, pl[g]);
 #pragma unroll
     for (int ga = 0; ga < 3; ga++) {
         uint32_t pi[BW];
-        load_plane<BW>(irow + off + ga * BW, pi);
+        load_plane<BW>(irow + off + ga * SW, pi);
 #pragma unroll
         for (int gb = 0; gb < 3; gb++) {
             uint32_t pj[BW];
-            load_plane<BW>(jrow + off + gb * BW, pj);
+            load_plane<BW>(jrow + off + gb * SW, pj);
 #pragma unroll
             for (int gc = 0; gc < 3; gc++) {
                 const int c = ga * 9 + gb * 3 + gc;
@@ -399,6 +469,15 @@ __device__ __forceinline__ void stagger_late_warps(int warp, int nwarps, int uni
     }
 }
 
+// once per unit: adopt the best bound any CTA has published for fold f
+__device__ __forceinline__ void refresh_threshold(SearchCtl *ctl, const SearchArgs &a, int f) {
+    const long long g = __ldcg(a.gthr + f);
+    if (g > *reinterpret_cast<volatile long long *>(&ctl->thr[f])) {
+        atomicMax(&ctl->thr[f], g);
+        if (a.training) atomicMax(&ctl->tq[f], thr_quotient(g, ctl->fl.A - ctl->fl.a_in[f]));
+    }
+}
+
 // common prologue: barriers, control block, counters, block descriptors
 template <bool SINGLE>
 __device__ __forceinline__ void search_init(SearchCtl *ctl, const SearchArgs &a, uint32_t *cnt_base, size_t cnt_words, uint16_t *desc) {
@@ -411,7 +490,10 @@ __device__ __forceinline__ void search_init(SearchCtl *ctl, const SearchArgs &a,
         mbar_fence_init();
         ctl->fl = *a.fl;
     }
-    if (tid < kMaxFolds) { ctl->thr[tid] = LLONG_MIN; ctl->lock[tid] = 0; ctl->cnt[tid] = 0; }
+    if (tid < kMaxFolds) {
+        ctl->thr[tid] = LLONG_MIN; ctl->lock[tid] = 0; ctl->cnt[tid] = 0;
+        ctl->tq[tid] = tid < a.fl->F ? INT_MIN : INT_MAX;      // folds past F (odd F, byte-counter pairs) never pass
+    }
     for (size_t x = tid; x < cnt_words; x += blockDim.x) cnt_base[x] = 0;   // halves that are never written must read 0
     if constexpr (!SINGLE) {
         const int nb = a.fl->nblocks;
@@ -450,6 +532,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
     search_init<SINGLE>(ctl, a, cnt_base, (sm.desc - sm.counters) / 4, desc);
 
     const int nblocks = ctl->fl.nblocks, cb = ctl->fl.cb, nchunks = ctl->fl.nchunks, roww = ctl->fl.row_words;
+    constexpr int SW = slot_words(BW);
     const int nwc = SINGLE ? nblocks / 4 : ctl->fl.F;
     const uint32_t row_bytes = (uint32_t) roww * 4;
 
@@ -481,7 +564,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
         }
     }
 
-    uint32_t *cnts = cnt_base + tid;          // + (c * nwc + k) * nthreads
+    constexpr int NC = 9;
+    uint32_t *cnts = cnt_base + (size_t) tid * counter_stride(NC, nwc);          // + k * NC + c
     uint32_t acc[9];
 #pragma unroll
     for (int c = 0; c < 9; c++) acc[c] = 0;
@@ -510,7 +594,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
         if (meta.x < 0) break;
         const int ch = meta.x, i0 = meta.y, j0 = meta.z;
         if (s == 0) stagger_late_warps(warp, TI, nblocks * 9 * (BW == 4 ? 24 : 34));
-        if (ch == 0 && warp == 0 && lane < ctl->fl.F) atomicMax(&ctl->thr[lane], __ldcg(a.gthr + lane));
+        if (ch == 0 && warp == 0 && lane < ctl->fl.F) refresh_threshold(ctl, a, lane);
 
         const uint32_t *sbase = reinterpret_cast<const uint32_t *>(smem_raw + sm.stage0 + (size_t) st * sm.stage_bytes);
         const uint32_t *irow = sbase + (size_t) warp * roww;
@@ -522,25 +606,25 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
                 uint32_t pk[9];
 #pragma unroll
                 for (int c = 0; c < 9; c++) pk[c] = 0;
-                const int off = (b4 - b_lo) * 3 * BW;
+                const int off = (b4 - b_lo) * 3 * SW;
                 single_block2<BW, 0>(irow + off, jrow + off, pk);
                 single_block2<BW, 1>(irow + off, jrow + off, pk);
                 single_block2<BW, 2>(irow + off, jrow + off, pk);
                 single_block2<BW, 3>(irow + off, jrow + off, pk);
                 const int k = b4 >> 2;
 #pragma unroll
-                for (int c = 0; c < 9; c++) cnts[(c * nwc + k) * nthreads] = pk[c];
+                for (int c = 0; c < 9; c++) cnts[k * 9 + c] = pk[c];
             }
         } else {
             for (int b = b_lo; b < b_hi; b++) {
-                const int off = (b - b_lo) * 3 * BW;
+                const int off = (b - b_lo) * 3 * SW;
                 uint32_t pj[3][BW];
 #pragma unroll
-                for (int g = 0; g < 3; g++) load_plane<BW>(jrow + off + g * BW, pj[g]);
+                for (int g = 0; g < 3; g++) load_plane<BW>(jrow + off + g * SW, pj[g]);
 #pragma unroll
                 for (int ga = 0; ga < 3; ga++) {
                     uint32_t pi[BW];
-                    load_plane<BW>(irow + off + ga * BW, pi);
+                    load_plane<BW>(irow + off + ga * SW, pi);
 #pragma unroll
                     for (int gb = 0; gb < 3; gb++) acc[ga * 3 + gb] = cell_count2_acc<BW, 1u>(pi, pj[gb], acc[ga * 3 + gb]);
                 }
@@ -549,7 +633,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
                     const int seg = d & 0x7fff;
 #pragma unroll
                     for (int c = 0; c < 9; c++) {
-                        reinterpret_cast<uint16_t *>(cnts + (c * nwc + (seg >> 1)) * nthreads)[seg & 1] = (uint16_t) acc[c];
+                        reinterpret_cast<uint16_t *>(cnts + (seg >> 1) * NC + c)[seg & 1] = (uint16_t) acc[c];
                         acc[c] = 0;
                     }
                 }
@@ -593,6 +677,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3_kernel(const Search
     search_init<SINGLE>(ctl, a, cnt_base, (sm.desc - sm.counters) / 4, desc);
 
     const int nblocks = ctl->fl.nblocks, cb = ctl->fl.cb, nchunks = ctl->fl.nchunks, roww = ctl->fl.row_words;
+    constexpr int SW = slot_words(BW);
     const int nwc = SINGLE ? nblocks / 4 : ctl->fl.F;
     const uint32_t row_bytes = (uint32_t) roww * 4;
     const int nkt = (a.nv + kTileJ - 1) / kTileJ;
@@ -627,7 +712,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3_kernel(const Search
         }
     }
 
-    uint32_t *cnts = cnt_base + tid;
+    constexpr int NC = 27;
+    uint32_t *cnts = cnt_base + (size_t) tid * counter_stride(NC, nwc);
     uint32_t acc[27];
 #pragma unroll
     for (int c = 0; c < 27; c++) acc[c] = 0;
@@ -657,7 +743,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3_kernel(const Search
         if (meta.x < 0) break;
         const int ch = meta.x, i = meta.y, j0 = meta.z, k0 = meta.w;
         if (s == 0) stagger_late_warps(warp, TJ, nblocks * 27 * (BW == 4 ? 24 : 34));
-        if (ch == 0 && warp == 0 && lane < ctl->fl.F) atomicMax(&ctl->thr[lane], __ldcg(a.gthr + lane));
+        if (ch == 0 && warp == 0 && lane < ctl->fl.F) refresh_threshold(ctl, a, lane);
 
         const uint32_t *sbase = reinterpret_cast<const uint32_t *>(smem_raw + sm.stage0 + (size_t) st * sm.stage_bytes);
         const uint32_t *irow = sbase;
@@ -670,29 +756,29 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3_kernel(const Search
                 uint32_t pk[27];
 #pragma unroll
                 for (int c = 0; c < 27; c++) pk[c] = 0;
-                const int off = (b4 - b_lo) * 3 * BW;
+                const int off = (b4 - b_lo) * 3 * SW;
                 single_block3<BW, 0>(irow + off, jrow + off, krow + off, pk);
                 single_block3<BW, 1>(irow + off, jrow + off, krow + off, pk);
                 single_block3<BW, 2>(irow + off, jrow + off, krow + off, pk);
                 single_block3<BW, 3>(irow + off, jrow + off, krow + off, pk);
                 const int k = b4 >> 2;
 #pragma unroll
-                for (int c = 0; c < 27; c++) cnts[(c * nwc + k) * nthreads] = pk[c];
+                for (int c = 0; c < 27; c++) cnts[k * 27 + c] = pk[c];
             }
         } else {
             for (int b = b_lo; b < b_hi; b++) {
-                const int off = (b - b_lo) * 3 * BW;
+                const int off = (b - b_lo) * 3 * SW;
                 uint32_t pl[3][BW];
 #pragma unroll
-                for (int g = 0; g < 3; g++) load_plane<BW>(krow + off + g * BW, pl[g]);
+                for (int g = 0; g < 3; g++) load_plane<BW>(krow + off + g * SW, pl[g]);
 #pragma unroll
                 for (int ga = 0; ga < 3; ga++) {
                     uint32_t pi[BW];
-                    load_plane<BW>(irow + off + ga * BW, pi);
+                    load_plane<BW>(irow + off + ga * SW, pi);
 #pragma unroll
                     for (int gb = 0; gb < 3; gb++) {
                         uint32_t pj[BW];
-                        load_plane<BW>(jrow + off + gb * BW, pj);
+                        load_plane<BW>(jrow + off + gb * SW, pj);
 #pragma unroll
                         for (int gc = 0; gc < 3; gc++) {
                             const int c = ga * 9 + gb * 3 + gc;
@@ -705,7 +791,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3_kernel(const Search
                     const int seg = d & 0x7fff;
 #pragma unroll
                     for (int c = 0; c < 27; c++) {
-                        reinterpret_cast<uint16_t *>(cnts + (c * nwc + (seg >> 1)) * nthreads)[seg & 1] = (uint16_t) acc[c];
+                        reinterpret_cast<uint16_t *>(cnts + (seg >> 1) * NC + c)[seg & 1] = (uint16_t) acc[c];
                         acc[c] = 0;
                     }
                 }

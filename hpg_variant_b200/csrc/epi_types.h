@@ -30,8 +30,11 @@ struct FoldLayout {
     int nseg;              // 2F
     int A, U;              // dataset-level class sizes (used by the high-risk rule, epistasis.c:37)
     int balanced;          // A == U: the float32 rule collapses to an integer test
+    int eqfolds;           // every fold holds as many cases as controls (a_in[f] == u_in[f]): with A == U the training score
+                           // of a fold is n_f * sum over cells of max(0, trA - trU), which the search kernels pre-filter on
     float ratio;           // (float)A / (float)U, mdr.c:52
     int bw;                // words per plane per block (4 or 8)
+    int w7;                // bw == 8 and only the first 7 words of a block hold samples (7 words compress to 3 POPC, not 4)
     int single;            // 1: every segment is exactly one block (block b <-> segment b, byte counters)
     int nblocks;           // real blocks along the sample axis (single: nseg rounded up to a multiple of 4)
     int cb;                // blocks per chunk (single: multiple of 4)

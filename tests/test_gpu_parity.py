@@ -76,6 +76,9 @@ SEARCH_SHAPES = [
     (90, 2000, 2000, 10, 20),    # c3-shaped samples (BW=8 single, u8)
     (50, 1500, 1100, 4, 30),     # u16 multi-block, unbalanced
     (37, 300, 200, 3, 700),      # rank > number of pairs: every pair comes back, sorted
+    (60, 720, 720, 3, 30),       # BW=8 single with 240 per segment: all 8 words of a block in use (no 7-word compress)
+    (40, 2500, 2500, 2, 30),     # 1250 per segment: 8-word multi-block layout, balanced pre-filter on 16-bit counters
+    (64, 90, 90, 5, 40),         # odd fold count: the last byte-counter word holds one real fold and one padding fold
 ]
 
 
@@ -103,6 +106,20 @@ def test_search_order3_matches_oracle(engine, oracle, nv, A, U, F, rank, subset)
     got = engine.search(3, subset, rank)
     want, _ = oracle.search(g, A, U, 3, fos, subset, rank, threads=8, num_folds=F)
     compare_models(got, want, 3)
+
+
+@pytest.mark.parametrize("order,nv,A,F", [(2, 80, 600, 6), (3, 22, 240, 4)])
+def test_search_balanced_classes_uneven_folds(engine, oracle, order, nv, A, F):
+    """A == U but folds that do not hold as many cases as controls: the balanced pre-filter must stand aside."""
+    rng = np.random.default_rng(17 + order)
+    g = synth.make_dataset(nv, A, A, seed=23 + order, order=order, missing=0.01, planted=1)
+    fos = np.concatenate([rng.permutation(A) % F, rng.integers(0, F, A)]).astype(np.int32)
+    engine.load_dataset(g, A, A)
+    engine.set_folds(F, fos)
+    for subset in (h.SUBSET_TRAINING, h.SUBSET_TESTING):
+        got = engine.search(order, subset, 30)
+        want, _ = oracle.search(g, A, A, order, fos, subset, 30, threads=8, num_folds=F)
+        compare_models(got, want, order)
 
 
 def test_search_ranges_partition(engine, oracle):
