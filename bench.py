@@ -372,7 +372,7 @@ def main():
                        "sharding": f"{world} contiguous combination-index ranges", "l2": "flushed between timed steps (256 MiB write)",
                        "layout": lay},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nv * S + lay["num_blocks"] * lay["block_words"] * 32 * 4),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nv * S + lay["num_blocks"] * (4 if lay["block_words"] == 3 else lay["block_words"]) * 32 * 4),
                     "d2h_bytes_per_step": rec_bytes, "steps": e2e_steps},
             "gpu_launches": int(launches),
             "roofline": roofline,

@@ -65,6 +65,8 @@ struct hpgv_epi_ctx {
     int64_t npos = 0;                     // bit positions per SNP row = nblocks * bw * 32
     std::vector<int32_t> perm;
     std::vector<uint16_t> blk;
+    bool tri_suppressed = false;          // the tri layout would fit but 4-word blocks were packed (order 3 / HPGV_NO_TRI)
+    std::vector<int32_t> fold_of_sample;  // the assignment of the last set_folds (the order-3 search re-packs without the tri layout)
     DevBuf<FoldLayout> d_fl;
     DevBuf<int32_t> d_perm;
     DevBuf<uint16_t> d_blk;
@@ -256,9 +258,21 @@ extern "C" int hpgv_epi_dataset_dims(const hpgv_epi_ctx *ctx, int64_t *nv, int *
 // ---------------------------------------------------------------------------------
 // folds
 // ---------------------------------------------------------------------------------
+static int apply_folds(hpgv_epi_ctx *ctx, int F, const int32_t *fold_of_sample, bool allow_tri);
+
 extern "C" int hpgv_epi_set_folds(hpgv_epi_ctx *ctx, int F, const int32_t *fold_of_sample) {
     if (!ctx || !fold_of_sample) return HPGV_E_ARG;
     if (!ctx->d_raw) FAIL(HPGV_E_STATE, "set_folds before a dataset was loaded");
+    std::vector<int32_t> keep(fold_of_sample, fold_of_sample + (size_t) ctx->A + ctx->U);
+    const char *no_tri = getenv("HPGV_NO_TRI");      // A/B switch for benchmarks: keep the 4-word layout
+    int rc = apply_folds(ctx, F, keep.data(), !(no_tri && no_tri[0] == '1'));
+    if (!rc) ctx->fold_of_sample.swap(keep);
+    return rc;
+}
+
+// Chooses the sample layout for a fold assignment and packs the planes.  allow_tri = false keeps the 4-word blocks
+// where the tri layout would apply (the order-3 kernel has no tri variant).
+static int apply_folds(hpgv_epi_ctx *ctx, int F, const int32_t *fold_of_sample, bool allow_tri) {
     if (F < 2 || F > kMaxFolds) FAIL(HPGV_E_ARG, "num_folds must be in [2, 32]");
     CK(cudaSetDevice(ctx->device));
     const int A = ctx->A, U = ctx->U, S = A + U;
@@ -306,8 +320,15 @@ extern "C" int hpgv_epi_set_folds(hpgv_epi_ctx *ctx, int F, const int32_t *fold_
     if (fl.single) nb = (nb + 3) / 4 * 4;              // byte counters are packed four blocks to a word
     if (nb > kMaxBlocks) FAIL(HPGV_E_UNSUPPORTED, "sample axis needs more than 4096 blocks (1M samples)");
     fl.nblocks = nb;
+    const bool tri_fits = fl.single && max_seg <= 100 && nb <= 24;
+    fl.tri = (allow_tri && tri_fits) ? 1 : 0;
+    ctx->tri_suppressed = tri_fits && !allow_tri;
+    if (fl.tri) {
+        fl.bw = 4;                                       // logical positions: word 3 of a block = its 4-bit tail
+        fl.cb = nb; fl.nchunks = 1;
+        fl.row_words = tri_row_words(nb);
+    } else {
     // chunks: a stage of the search kernels holds (16 + 32 + 1) chunk rows; keep it within 48 KB
-    {
         const int block_bytes = 3 * fl.bw * 4;
         int cb_max = std::max(1, (48 * 1024 / (kMaxWarps + kTileJ + 1) - 16) / block_bytes);
         if (fl.single) cb_max = std::max(4, cb_max / 4 * 4);
@@ -561,6 +582,16 @@ static int do_search(hpgv_epi_ctx *ctx, int order, int eval_subset, int rank, ui
     if (last > total) last = total;
     if (first > last) first = last;
 
+    // the tri layout exists for the order-2 kernel only: re-pack with 4-word blocks for order 3 (and back for order 2)
+    if (!ctx->fold_of_sample.empty()) {
+        const char *no_tri = getenv("HPGV_NO_TRI");
+        const bool want_tri = order == 2 && !(no_tri && no_tri[0] == '1');
+        if ((ctx->fl.tri != 0) != want_tri && (ctx->fl.tri || ctx->tri_suppressed)) {
+            const std::vector<int32_t> fos = ctx->fold_of_sample;
+            int rc = apply_folds(ctx, ctx->fl.F, fos.data(), want_tri);
+            if (rc) return rc;
+        }
+    }
     const FoldLayout &fl = ctx->fl;
     const int F = fl.F;
     SearchArgs args{};
@@ -573,6 +604,10 @@ static int do_search(hpgv_epi_ctx *ctx, int order, int eval_subset, int rank, ui
     args.rank = rank;
     args.first = first;
     args.last = last;
+    {
+        const char *st = getenv("HPGV_STAGGER");
+        args.stagger = !(st && st[0] == '0');
+    }
 
     const SearchShape shape = pick_shape(ctx, order, rank);
     if (shape.nthreads == 0)
@@ -601,7 +636,9 @@ static int do_search(hpgv_epi_ctx *ctx, int order, int eval_subset, int rank, ui
         else grid = balanced ? launch_search(ctx, KERNEL<8, false, true>, shape, args, F, rank)      \
                              : launch_search(ctx, KERNEL<8, false, false>, shape, args, F, rank);    \
     } while (0)
-    if (order == 2) HPGV_LAUNCH(search2_kernel);
+    if (order == 2 && fl.tri) grid = balanced ? launch_search(ctx, search2_kernel<3, true, true>, shape, args, F, rank)
+                                              : launch_search(ctx, search2_kernel<3, true, false>, shape, args, F, rank);
+    else if (order == 2) HPGV_LAUNCH(search2_kernel);
     else HPGV_LAUNCH(search3_kernel);
 #undef HPGV_LAUNCH
     if (grid < 0) return grid;
@@ -744,7 +781,7 @@ extern "C" int hpgv_epi_last_search_ms(hpgv_epi_ctx *ctx, float *ms, int *grid) 
 extern "C" int hpgv_epi_layout(const hpgv_epi_ctx *ctx, hpgv_epi_layout_t *out) {
     if (!ctx || !out) return HPGV_E_ARG;
     if (!ctx->folds_set) return HPGV_E_STATE;
-    out->num_folds = ctx->fl.F; out->num_segments = ctx->fl.nseg; out->num_blocks = ctx->fl.nblocks; out->block_words = ctx->fl.bw;
+    out->num_folds = ctx->fl.F; out->num_segments = ctx->fl.nseg; out->num_blocks = ctx->fl.nblocks; out->block_words = ctx->fl.tri ? 3 : ctx->fl.bw;
     out->num_chunks = ctx->fl.nchunks; out->chunk_blocks = ctx->fl.cb; out->row_words = ctx->fl.row_words;
     out->count_bits = ctx->fl.single ? 8 : 16;
     out->plane_bytes = (int64_t) ctx->plane_words * 4;

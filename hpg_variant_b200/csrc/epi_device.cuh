@@ -149,6 +149,52 @@ __host__ __device__ __forceinline__ int64_t plane_word(const FoldLayout &fl, int
     return ((int64_t) ch * snp_pad + snp) * fl.row_words + (bl * 3 + g) * fl.bw + w;
 }
 
+// ---- tri layout (FoldLayout::tri) ---------------------------------------------
+// One chunk.  A row is ngroups = nblocks/4 groups of 36 words followed by the tails:
+//   main word (b, g, w), w < 3 : (b/4)*36 + g*12 + (b%4)*3 + w      (a group = 3 planes x 4 blocks x 3 words = 9 LDS.128)
+//   tail word (m, g), m = b/8  : ngroups*36 + m*4 + g               (one LDS.128 = the three planes of eight blocks' tails)
+// The tail of block b = 4k + q sits in the nibble that the byte counters want: counter word k keeps block q in byte
+// group_shift(q)/8; tail word m = k/2 keeps it in nibble 2*byte + (k&1), so that after a nibble-wise popcount n,
+// n & 0x0F0F0F0F adds to counter word 2m and (n >> 4) & 0x0F0F0F0F to counter word 2m + 1.
+__host__ __device__ constexpr uint32_t group_shift(int q) { return q == 0 ? 0u : (q == 1 ? 16u : (q == 2 ? 8u : 24u)); }
+__host__ __device__ __forceinline__ int tri_word_off(int b, int g, int w) { return (b >> 2) * 36 + g * 12 + (b & 3) * 3 + w; }
+__host__ __device__ __forceinline__ int tri_tail_off(int nblocks, int b, int g) { return (nblocks >> 2) * 36 + (b >> 3) * 4 + g; }
+__host__ __device__ __forceinline__ int tri_tail_shift(int b) { return (int) (group_shift(b & 3) / 8 * 2 + ((b >> 2) & 1)) * 4; }
+__host__ __device__ __forceinline__ int tri_row_words(int nblocks) {
+    int rw = (nblocks >> 2) * 36 + ((nblocks + 7) >> 3) * 4;
+    if ((rw / 4) % 2 == 0) rw += 4;
+    return rw;
+}
+
+// logical word w (of fl.bw) of plane g of block b of one SNP, whatever the physical layout
+__device__ __forceinline__ uint32_t logical_word(const uint32_t *__restrict__ planes, const FoldLayout &fl, int64_t snp_pad, int b,
+                                                 int64_t snp, int g, int w) {
+    if (fl.tri) {
+        const uint32_t *row = planes + snp * fl.row_words;
+        if (w < 3) return row[tri_word_off(b, g, w)];
+        return (row[tri_tail_off(fl.nblocks, b, g)] >> tri_tail_shift(b)) & 0xFu;
+    }
+    return planes[plane_word(fl, snp_pad, b, snp, g, w)];
+}
+
+// nibble-wise popcount of x added to two packed byte counters: even nibbles -> lo, odd nibbles -> hi
+__device__ __forceinline__ void tail_count_acc(uint32_t x, uint32_t &lo, uint32_t &hi) {
+    x = x - ((x >> 1) & 0x55555555u);
+    x = (x & 0x33333333u) + ((x >> 2) & 0x33333333u);
+    const uint32_t e = x & 0x0F0F0F0Fu;
+    lo += e;
+    hi += (x - e) >> 4;
+}
+
+// one block of the tri layout: 3 words -> 2 POPC, weighted into byte SHIFT/8 of the packed counter
+template <uint32_t K>
+__device__ __forceinline__ uint32_t tri_count2_acc(const uint32_t *a, const uint32_t *b, uint32_t acc) {
+    const uint32_t x0 = a[0] & b[0], x1 = a[1] & b[1], x2 = a[2] & b[2];
+    acc = mad_const<K>(__popc(xor3(x0, x1, x2)), acc);
+    acc = mad_const<2 * K>(__popc(maj3(x0, x1, x2)), acc);
+    return acc;
+}
+
 // ----------------------------------------------------------------------------
 // High-risk rule -- bit-exact with mdr_high_risk_combinations2 (mdr.c:45-75).
 //

@@ -51,7 +51,16 @@ __global__ void pack_planes_kernel(const uint8_t *__restrict__ raw, int64_t nv, 
     const uint32_t m0 = __ballot_sync(0xffffffffu, g == 0);
     const uint32_t m1 = __ballot_sync(0xffffffffu, g == 1);
     const uint32_t m2 = __ballot_sync(0xffffffffu, g == 2);
-    if (lane < 3) planes[plane_word(fl, snp_pad, b, snp, lane, w)] = lane == 0 ? m0 : (lane == 1 ? m1 : m2);
+    const uint32_t mine = lane == 0 ? m0 : (lane == 1 ? m1 : m2);
+    if (lane >= 3) return;
+    if (fl.tri) {
+        // the planes were zeroed: the tails of eight blocks are OR-ed into one word
+        uint32_t *row = planes + snp * fl.row_words;
+        if (w < 3) row[tri_word_off(b, lane, w)] = mine;
+        else if (mine & 0xFu) atomicOr(row + tri_tail_off(fl.nblocks, b, lane), (mine & 0xFu) << tri_tail_shift(b));
+    } else {
+        planes[plane_word(fl, snp_pad, b, snp, lane, w)] = mine;
+    }
 }
 
 // Inverse of the packer for one SNP: byte masks in the reference's layout
@@ -67,7 +76,7 @@ __global__ void unpack_masks_kernel(const uint32_t *__restrict__ planes, int64_t
     const int b = (int) (pos / (32 * fl.bw)), w = (int) ((pos / 32) % fl.bw), bit = (int) (pos & 31);
     const int dst = col < A ? col : a_pad + (col - A);
     for (int g = 0; g < 3; g++) {
-        const uint32_t word = planes[plane_word(fl, snp_pad, b, snp, g, w)];
+        const uint32_t word = logical_word(planes, fl, snp_pad, b, snp, g, w);
         out[(int64_t) g * s_pad + dst] = ((word >> bit) & 1u) ? 0xFF : 0x00;
     }
 }
@@ -415,9 +424,8 @@ __device__ __forceinline__ void epilogue_balanced(SearchCtl *ctl, const SearchAr
     else epilogue_balanced_t<NCELLS, U8, false>(ctl, a, lists, cnts, nwc, nthreads, valid, si, sj, sk, lane);
 }
 
-// shift of the byte counter of block q (0..3) of a four-block group: segments (2k A, 2k U, 2k+1 A, 2k+1 U)
-// land in bytes (0, 2, 1, 3), i.e. the word reads (A_2k, A_2k+1, U_2k, U_2k+1)
-__host__ __device__ constexpr uint32_t group_shift(int q) { return q == 0 ? 0u : (q == 1 ? 16u : (q == 2 ? 8u : 24u)); }
+// group_shift(q) (epi_device.cuh): shift of the byte counter of block q (0..3) of a four-block group: segments
+// (2k A, 2k U, 2k+1 A, 2k+1 U) land in bytes (0, 2, 1, 3), i.e. the word reads (A_2k, A_2k+1, U_2k, U_2k+1)
 
 // block Q (0..3) of a four-block group, single-block segments: the nine (27) cell counts go to byte group_shift(Q) of pk[]
 template <int BW, int Q>
@@ -453,6 +461,37 @@ __device__ __forceinline__ void single_block3(const uint32_t *irow, const uint32
                 const int c = ga * 9 + gb * 3 + gc;
                 pk[c] = cell_count3_acc<BW, (1u << group_shift(Q))>(pi, pj, pl[gc], pk[c]);
             }
+        }
+    }
+}
+
+// one group (four blocks) of the tri layout: 36 words of the j row stay in registers, the i row is read plane by plane
+__device__ __forceinline__ void tri_group2(const uint32_t *ig, const uint32_t *jg, uint32_t (&pk)[9]) {
+    uint32_t pj[3][12];
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const uint4 t = *reinterpret_cast<const uint4 *>(jg + g * 12 + 4 * q);
+            pj[g][4 * q] = t.x; pj[g][4 * q + 1] = t.y; pj[g][4 * q + 2] = t.z; pj[g][4 * q + 3] = t.w;
+        }
+    }
+#pragma unroll
+    for (int ga = 0; ga < 3; ga++) {
+        uint32_t pi[12];
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const uint4 t = *reinterpret_cast<const uint4 *>(ig + ga * 12 + 4 * q);
+            pi[4 * q] = t.x; pi[4 * q + 1] = t.y; pi[4 * q + 2] = t.z; pi[4 * q + 3] = t.w;
+        }
+#pragma unroll
+        for (int gb = 0; gb < 3; gb++) {
+            uint32_t acc = pk[ga * 3 + gb];
+            acc = tri_count2_acc<(1u << group_shift(0))>(pi + 0, pj[gb] + 0, acc);
+            acc = tri_count2_acc<(1u << group_shift(1))>(pi + 3, pj[gb] + 3, acc);
+            acc = tri_count2_acc<(1u << group_shift(2))>(pi + 6, pj[gb] + 6, acc);
+            acc = tri_count2_acc<(1u << group_shift(3))>(pi + 9, pj[gb] + 9, acc);
+            pk[ga * 3 + gb] = acc;
         }
     }
 }
@@ -593,7 +632,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
         const int4 meta = ctl->meta[s % 3];
         if (meta.x < 0) break;
         const int ch = meta.x, i0 = meta.y, j0 = meta.z;
-        if (s == 0) stagger_late_warps(warp, TI, nblocks * 9 * (BW == 4 ? 24 : 34));
+        if (s == 0 && a.stagger) stagger_late_warps(warp, TI, nblocks * 9 * (BW == 3 ? 18 : (BW == 4 ? 24 : 34)));
         if (ch == 0 && warp == 0 && lane < ctl->fl.F) refresh_threshold(ctl, a, lane);
 
         const uint32_t *sbase = reinterpret_cast<const uint32_t *>(smem_raw + sm.stage0 + (size_t) st * sm.stage_bytes);
@@ -601,7 +640,33 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
         const uint32_t *jrow = sbase + (size_t) (TI + lane) * roww;
         const int b_lo = ch * cb, b_hi = min(nblocks, b_lo + cb);
 
-        if constexpr (SINGLE) {
+        if constexpr (BW == 3) {
+            // tri layout (one chunk): two groups of four blocks share a tail word
+            const int ngroups = nblocks >> 2;
+            const uint32_t *itail = irow + ngroups * 36, *jtail = jrow + ngroups * 36;
+            for (int m = 0; 2 * m < ngroups; m++) {
+                uint32_t pk0[9], pk1[9];
+#pragma unroll
+                for (int c = 0; c < 9; c++) { pk0[c] = 0; pk1[c] = 0; }
+                {
+                    const uint4 tj = *reinterpret_cast<const uint4 *>(jtail + 4 * m);
+                    const uint4 ti = *reinterpret_cast<const uint4 *>(itail + 4 * m);
+                    const uint32_t tjv[3] = {tj.x, tj.y, tj.z}, tiv[3] = {ti.x, ti.y, ti.z};
+#pragma unroll
+                    for (int ga = 0; ga < 3; ga++)
+#pragma unroll
+                        for (int gb = 0; gb < 3; gb++) tail_count_acc(tiv[ga] & tjv[gb], pk0[ga * 3 + gb], pk1[ga * 3 + gb]);
+                }
+                tri_group2(irow + (2 * m) * 36, jrow + (2 * m) * 36, pk0);
+#pragma unroll
+                for (int c = 0; c < 9; c++) cnts[(2 * m) * 9 + c] = pk0[c];
+                if (2 * m + 1 < ngroups) {
+                    tri_group2(irow + (2 * m + 1) * 36, jrow + (2 * m + 1) * 36, pk1);
+#pragma unroll
+                    for (int c = 0; c < 9; c++) cnts[(2 * m + 1) * 9 + c] = pk1[c];
+                }
+            }
+        } else if constexpr (SINGLE) {
             for (int b4 = b_lo; b4 < b_hi; b4 += 4) {
                 uint32_t pk[9];
 #pragma unroll
@@ -742,7 +807,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3_kernel(const Search
         const int4 meta = ctl->meta[s % 3];
         if (meta.x < 0) break;
         const int ch = meta.x, i = meta.y, j0 = meta.z, k0 = meta.w;
-        if (s == 0) stagger_late_warps(warp, TJ, nblocks * 27 * (BW == 4 ? 24 : 34));
+        if (s == 0 && a.stagger) stagger_late_warps(warp, TJ, nblocks * 27 * (BW == 4 ? 24 : 34));
         if (ch == 0 && warp == 0 && lane < ctl->fl.F) refresh_threshold(ctl, a, lane);
 
         const uint32_t *sbase = reinterpret_cast<const uint32_t *>(smem_raw + sm.stage0 + (size_t) st * sm.stage_bytes);
@@ -1011,7 +1076,7 @@ __global__ void eval_kernel(const uint32_t *__restrict__ planes, const uint16_t 
             for (int o = order - 1; o >= 0; o--) {
                 const int g = rem % 3;
                 rem /= 3;
-                v &= planes[plane_word(fl, snp_pad, b, s[o], g, w)];
+                v &= logical_word(planes, fl, snp_pad, b, s[o], g, w);
             }
             atomicAdd(&segcnt[seg * C + c], __popc(v));
         }

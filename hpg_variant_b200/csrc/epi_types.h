@@ -24,7 +24,7 @@ constexpr int kMaxWarps  = 16;            // consumer warps per CTA = i (or j) r
 // chunk-major, [chunk][snp][row_words] with row_words = cb*3*bw (+ padding so
 // that row_words/4 is odd: 32 lanes reading 32 consecutive rows with LDS.128
 // then hit 8 distinct 16-byte bank groups per quarter-warp).  Inside a row:
-// word (bl, g, w) at (bl*3 + g)*bw + w.
+// word (bl, g, w) at (bl*3 + g)*bw + w  (tri layout: see tri_word_off / tri_tail_off).
 struct FoldLayout {
     int F;                 // folds
     int nseg;              // 2F
@@ -36,6 +36,10 @@ struct FoldLayout {
     int bw;                // words per plane per block (4 or 8)
     int w7;                // bw == 8 and only the first 7 words of a block hold samples (7 words compress to 3 POPC, not 4)
     int single;            // 1: every segment is exactly one block (block b <-> segment b, byte counters)
+    int tri;               // single && every segment <= 100 samples && <= 24 blocks: three full words per plane and block plus a
+                           // 4-bit tail per segment, the tails of eight segments sharing one word (see tri_* in epi_device.cuh):
+                           // 3 words compress to 2 POPC, the tails are counted with nibble-wise adds on the ALU.  Logical
+                           // bit positions stay those of bw = 4 (word 3 of a block = its tail, bits 0..3).
     int nblocks;           // real blocks along the sample axis (single: nseg rounded up to a multiple of 4)
     int cb;                // blocks per chunk (single: multiple of 4)
     int nchunks;
@@ -73,6 +77,7 @@ struct SearchArgs {
     Cand *lists;                // [grid][F][rank]
     int *list_cnt;              // [grid][F]
     long long *gthr;            // [F] global score threshold (lower bound of the N-th best)
+    int stagger;                // delay the upper half of the warps once by half a unit (HPGV_STAGGER=0 turns it off)
 };
 
 }  // namespace hpgv

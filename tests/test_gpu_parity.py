@@ -45,6 +45,9 @@ SHAPES = [
     (8, 1300, 900, 3),     # BW=8, 2 blocks per segment (434, 300), u16 counters, unbalanced
     (7, 5000, 5000, 2),    # many blocks per segment, u16
     (6, 33, 17, 2),        # ragged tiny
+    (10, 120, 115, 3),     # tri layout, eight blocks, tails empty
+    (9, 360, 345, 3),      # BW=4 without the tri layout (115..120 per segment), unbalanced
+    (8, 397, 400, 4),      # tri layout with the 4-bit tails in use (99..100 per segment)
 ]
 
 
@@ -79,6 +82,11 @@ SEARCH_SHAPES = [
     (60, 720, 720, 3, 30),       # BW=8 single with 240 per segment: all 8 words of a block in use (no 7-word compress)
     (40, 2500, 2500, 2, 30),     # 1250 per segment: 8-word multi-block layout, balanced pre-filter on 16-bit counters
     (64, 90, 90, 5, 40),         # odd fold count: the last byte-counter word holds one real fold and one padding fold
+    (60, 360, 360, 3, 40),       # BW=4 proper (120 per segment: too long for the tri layout), balanced
+    (50, 230, 460, 4, 40),       # BW=4 proper, unbalanced (57..58 / 115 per segment)
+    (40, 130, 130, 13, 30),      # 28 blocks: too many for the tri layout, 4-word blocks with short segments
+    (50, 985, 970, 10, 40),      # tri layout, unbalanced, tails partly filled (98..99 / 97 per segment)
+    (48, 1200, 1200, 12, 40),    # tri layout at its limits: 24 blocks of exactly 100 samples
 ]
 
 
@@ -122,6 +130,30 @@ def test_search_balanced_classes_uneven_folds(engine, oracle, order, nv, A, F):
         compare_models(got, want, order)
 
 
+def test_tri_layout_equals_four_word_layout(engine, monkeypatch):
+    """The tri layout (3 words + shared 4-bit tails, 2 POPC per block) and the plain 4-word layout give the same bytes."""
+    nv, A, U, F, rank = 150, 1000, 1000, 10, 50
+    g = synth.make_dataset(nv, A, U, seed=77, missing=0.01, planted=2)
+    fos = random_folds(np.random.default_rng(9), A, U, F)
+    engine.load_dataset(g, A, U)
+    engine.set_folds(F, fos)
+    assert engine.layout()["block_words"] == 3
+    tri = [engine.search(2, s, rank) for s in (h.SUBSET_TRAINING, h.SUBSET_TESTING)]
+    o3 = engine.search(3, h.SUBSET_TRAINING, 10, 0, 20000)        # order 3 re-packs with 4-word blocks ...
+    assert engine.layout()["block_words"] == 4
+    again = engine.search(2, h.SUBSET_TRAINING, rank)             # ... and order 2 goes back to the tri layout
+    assert engine.layout()["block_words"] == 3
+    assert again.tobytes() == tri[0].tobytes()
+    monkeypatch.setenv("HPGV_NO_TRI", "1")
+    engine.set_folds(F, fos)
+    assert engine.layout()["block_words"] == 4
+    plain = [engine.search(2, s, rank) for s in (h.SUBSET_TRAINING, h.SUBSET_TESTING)]
+    o3b = engine.search(3, h.SUBSET_TRAINING, 10, 0, 20000)
+    for a, b in zip(tri, plain):
+        assert a.tobytes() == b.tobytes()
+    assert o3.tobytes() == o3b.tobytes()
+
+
 def test_search_ranges_partition(engine, oracle):
     """Contiguous index ranges (the multi-GPU sharding) merged on the GPU == one full search."""
     import torch
@@ -145,9 +177,10 @@ def test_search_ranges_partition(engine, oracle):
         compare_models(p, want, 2)
 
 
-def test_packer_roundtrip(engine, oracle):
-    """unpack(pack(bytes)) == set_genotypes_masks of the reference (model.c:28-74), folds shuffled."""
-    nv, A, U, F = 5, 77, 130, 7
+@pytest.mark.parametrize("nv,A,U,F", [(5, 77, 130, 7), (4, 400, 395, 4), (3, 240, 230, 2), (3, 900, 2600, 3)])
+def test_packer_roundtrip(engine, oracle, nv, A, U, F):
+    """unpack(pack(bytes)) == set_genotypes_masks of the reference (model.c:28-74), folds shuffled.
+    Layouts: tri without / with tails, 4-word blocks, 8-word multi-block."""
     g = synth.make_dataset(nv, A, U, seed=3, missing=0.05, planted=0)
     fos = random_folds(np.random.default_rng(2), A, U, F)
     engine.load_dataset(g, A, U)
