@@ -77,6 +77,7 @@ struct hpgv_epi_ctx {
     DevBuf<Cand> d_lists;
     DevBuf<int> d_list_cnt;
     DevBuf<long long> d_gthr;
+    DevBuf<int> d_hist, d_hmax;
     DevBuf<int64_t> d_prefix;
     DevBuf<int32_t> d_jt0;
     DevBuf<hpgv_epi_model_t> d_out;
@@ -111,8 +112,8 @@ struct hpgv_epi_ctx {
 // ---------------------------------------------------------------------------------
 // reset kernel: global thresholds
 // ---------------------------------------------------------------------------------
-__global__ void reset_search_kernel(long long *gthr) {
-    if (threadIdx.x < kMaxFolds) gthr[threadIdx.x] = LLONG_MIN;
+__global__ void reset_search_kernel(long long *gthr, int *ghmax) {
+    if (threadIdx.x < kMaxFolds) { gthr[threadIdx.x] = LLONG_MIN; ghmax[threadIdx.x] = -1; }
 }
 
 // ---------------------------------------------------------------------------------
@@ -162,7 +163,7 @@ extern "C" void hpgv_epi_destroy(hpgv_epi_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     ctx->raw_owned.release(); ctx->d_fl.release(); ctx->d_perm.release(); ctx->d_blk.release(); ctx->d_planes.release();
-    ctx->d_lists.release(); ctx->d_list_cnt.release(); ctx->d_gthr.release();
+    ctx->d_lists.release(); ctx->d_list_cnt.release(); ctx->d_gthr.release(); ctx->d_hist.release(); ctx->d_hmax.release();
     ctx->d_prefix.release(); ctx->d_jt0.release(); ctx->d_out.release(); ctx->d_merge_in.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -544,11 +545,20 @@ static int launch_search(hpgv_epi_ctx *ctx, K kernel, const SearchShape &shape, 
     CK(ctx->d_lists.reserve((size_t) grid * F * rank));
     CK(ctx->d_list_cnt.reserve((size_t) grid * F));
     CK(ctx->d_gthr.reserve(kMaxFolds));
+    CK(ctx->d_hmax.reserve(kMaxFolds));
     args.lists = ctx->d_lists.p;
     args.list_cnt = ctx->d_list_cnt.p;
     args.gthr = ctx->d_gthr.p;
+    args.ghmax = ctx->d_hmax.p;
+    args.ghist = nullptr;
+    if (args.use_hist) {
+        const size_t bins = (size_t) F * args.hist_bins;
+        CK(ctx->d_hist.reserve(bins));
+        CK(cudaMemsetAsync(ctx->d_hist.p, 0, bins * sizeof(int), ctx->stream));
+        args.ghist = ctx->d_hist.p;
+    }
     args.lists_in_smem = shape.lists_in_smem ? 1 : 0;
-    reset_search_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_gthr.p);
+    reset_search_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_gthr.p, ctx->d_hmax.p);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     kernel<<<(unsigned) grid, shape.nthreads, shape.smem, ctx->stream>>>(args);
@@ -622,6 +632,12 @@ static int do_search(hpgv_epi_ctx *ctx, int order, int eval_subset, int rank, ui
 
     // the packed-pair epilogue needs A == U (r = 1: the float32 rule is exact) and 16-bit class sizes
     const bool balanced = fl.balanced && fl.A <= 65535;
+    {
+        // score histogram: the pre-filter's conditions (epilogue_balanced_t) and the order-2 kernel's step modes
+        const char *hs = getenv("HPGV_HIST");
+        args.use_hist = (order == 2 && balanced && fl.eqfolds && args.training && !(hs && hs[0] == '0')) ? 1 : 0;
+        args.hist_bins = fl.A + 1;
+    }
     int grid = 0;
 #define HPGV_LAUNCH(KERNEL)                                                                          \
     do {                                                                                             \

@@ -333,8 +333,20 @@ __device__ __forceinline__ int dp4a_us(uint32_t a8x4, uint32_t b8x4, int c) {
 // with D_c = totA_c - totU_c and d_cf = inA_cf - inU_cf: one IDP (dot product with +-1 bytes) and one VIMNMX.RELU per
 // cell and fold, no unpacking, no risk mask.  Returns whether any fold of this thread's tuple reaches the fold's bound
 // ctl->tq; only then is the exact epilogue (masks, TP/FP, BA, list offer) run.  A stale (lower) bound only costs time.
+//
+// mode (per step, from the producer): bit 0 = count the scores that reach the bound into the global histogram (every
+// score when bit 1 is clear), bit 1 = candidates are offered to the lists.  See hist_threshold().
+constexpr int kModeCount = 1, kModeOffer = 2;
+
+__device__ __forceinline__ void hist_count(const SearchArgs &a, int f, int t, bool on) {
+    if (on) atomicAdd(a.ghist + (size_t) f * a.hist_bins + t, 1);
+    const int m = __reduce_max_sync(0xffffffffu, on ? t : -1);
+    if ((threadIdx.x & 31) == 0 && m >= 0 && m > __ldcg(a.ghmax + f)) atomicMax(a.ghmax + f, m);
+}
+
 template <int NCELLS, bool U8>
-__device__ __forceinline__ bool balanced_prefilter(const SearchCtl *ctl, const uint32_t *cnts, int nwc, int nthreads) {
+__device__ __forceinline__ bool balanced_prefilter(const SearchCtl *ctl, const SearchArgs &a, const uint32_t *cnts, int nwc, bool valid,
+                                                   int mode) {
     int D[NCELLS];
 #pragma unroll
     for (int c = 0; c < NCELLS; c++) D[c] = 0;
@@ -356,7 +368,14 @@ __device__ __forceinline__ bool balanced_prefilter(const SearchCtl *ctl, const u
                 t0 += max(dp4a_us(w, 0x000100FFu, D[c]), 0);
                 t1 += max(dp4a_us(w, 0x0100FF00u, D[c]), 0);
             }
-            pass |= (t0 >= tq[2 * k]) | (t1 >= tq[2 * k + 1]);
+            const bool p0 = t0 >= tq[2 * k], p1 = t1 >= tq[2 * k + 1];
+            pass |= p0 | p1;
+            if (mode & kModeCount) {
+                const bool all = !(mode & kModeOffer);
+                const bool c0 = valid && (p0 || all), c1 = valid && (p1 || all) && 2 * k + 1 < ctl->fl.F;
+                if (__any_sync(0xffffffffu, c0)) hist_count(a, 2 * k, t0, c0);
+                if (__any_sync(0xffffffffu, c1)) hist_count(a, 2 * k + 1, t1, c1);
+            }
         } else {                                              // w = A_k | U_k << 16
             int t = 0;
 #pragma unroll
@@ -364,7 +383,12 @@ __device__ __forceinline__ bool balanced_prefilter(const SearchCtl *ctl, const u
                 const uint32_t w = cnts[k * NCELLS + c];
                 t += max(dp2a_lo_us(w, 0x000001FFu, D[c]), 0);
             }
-            pass |= t >= tq[k];
+            const bool p = t >= tq[k];
+            pass |= p;
+            if (mode & kModeCount) {
+                const bool c = valid && (p || !(mode & kModeOffer));
+                if (__any_sync(0xffffffffu, c)) hist_count(a, k, t, c);
+            }
         }
     }
     return pass;
@@ -375,11 +399,12 @@ __device__ __forceinline__ bool balanced_prefilter(const SearchCtl *ctl, const u
 // risky <=> trA >= trU and trA > 0 (see high_risk()).
 template <int NCELLS, bool U8, bool TRAINING>
 __device__ __forceinline__ void epilogue_balanced_t(SearchCtl *ctl, const SearchArgs &a, Cand *lists, const uint32_t *cnts, int nwc,
-                                                    int nthreads, bool valid, int si, int sj, int sk, int lane) {
+                                                    int nthreads, bool valid, int si, int sj, int sk, int lane, int mode) {
     const int nfolds = ctl->fl.F;
     if constexpr (TRAINING) {
         if (ctl->fl.eqfolds) {
-            const bool pass = balanced_prefilter<NCELLS, U8>(ctl, cnts, nwc, nthreads);
+            const bool pass = balanced_prefilter<NCELLS, U8>(ctl, a, cnts, nwc, valid, mode);
+            if (!(mode & kModeOffer)) return;
             if (!__any_sync(0xffffffffu, pass && valid)) return;
         }
     }
@@ -419,9 +444,9 @@ __device__ __forceinline__ void epilogue_balanced_t(SearchCtl *ctl, const Search
 }
 template <int NCELLS, bool U8>
 __device__ __forceinline__ void epilogue_balanced(SearchCtl *ctl, const SearchArgs &a, Cand *lists, const uint32_t *cnts, int nwc,
-                                                  int nthreads, bool valid, int si, int sj, int sk, int lane) {
-    if (a.training) epilogue_balanced_t<NCELLS, U8, true>(ctl, a, lists, cnts, nwc, nthreads, valid, si, sj, sk, lane);
-    else epilogue_balanced_t<NCELLS, U8, false>(ctl, a, lists, cnts, nwc, nthreads, valid, si, sj, sk, lane);
+                                                  int nthreads, bool valid, int si, int sj, int sk, int lane, int mode) {
+    if (a.training) epilogue_balanced_t<NCELLS, U8, true>(ctl, a, lists, cnts, nwc, nthreads, valid, si, sj, sk, lane, mode);
+    else epilogue_balanced_t<NCELLS, U8, false>(ctl, a, lists, cnts, nwc, nthreads, valid, si, sj, sk, lane, mode);
 }
 
 // group_shift(q) (epi_device.cuh): shift of the byte counter of block q (0..3) of a four-block group: segments
@@ -517,6 +542,34 @@ __device__ __forceinline__ void refresh_threshold(SearchCtl *ctl, const SearchAr
     }
 }
 
+// Once per unit and fold (one warp each): the largest score T such that at least N pairs counted in the global
+// histogram reach it.  Those pairs are distinct members of this search's range, so no pair below T can be among the
+// N best of the fold: T becomes the bound of the CTA's pre-filter and list.  A stale histogram only gives a lower T.
+__device__ __forceinline__ void hist_threshold(SearchCtl *ctl, const SearchArgs &a, int f, int lane) {
+    const int hmax = __ldcg(a.ghmax + f);
+    const int cur = *reinterpret_cast<volatile int *>(&ctl->tq[f]);
+    const int lo = max(cur, 0);                      // scores below the current bound are not counted any more
+    if (hmax < lo) return;
+    const int *h = a.ghist + (size_t) f * a.hist_bins;
+    int cum = 0, T = INT_MIN;
+    for (int base = hmax; base >= lo; base -= 32) {
+        const int t = base - lane;                   // lane 0 reads the highest score of the window
+        int incl = (t >= lo) ? __ldcg(h + t) : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += n;
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, cum + incl >= a.rank);
+        if (hit) { T = base - (__ffs(hit) - 1); break; }
+        cum += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0 && T != INT_MIN && T > cur) {
+        atomicMax(&ctl->tq[f], T);
+        atomicMax(&ctl->thr[f], (long long) T * (ctl->fl.A - ctl->fl.a_in[f]));
+    }
+}
+
 // common prologue: barriers, control block, counters, block descriptors
 template <bool SINGLE>
 __device__ __forceinline__ void search_init(SearchCtl *ctl, const SearchArgs &a, uint32_t *cnt_base, size_t cnt_words, uint16_t *desc) {
@@ -583,6 +636,24 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
         cur_i0 = (a.it0 + grp) * TI;
         cur_j0 = (a.unit_jt0[grp] + (int) (u - a.unit_prefix[grp])) * kTileJ;
     };
+    // With the score histogram the CTA's first unit is only counted (no list has a bound yet: every pair would be
+    // offered) and run again, offers only, after the last unit -- by then the bound keeps nearly all of it out.
+    int redo = 0;                                   // 0: main pass, 1: re-running the first unit, 2: no more work
+    auto mode_of = [&]() { return !a.use_hist || redo ? kModeOffer : (u == (long long) blockIdx.x ? kModeCount : (kModeCount | kModeOffer)); };
+    auto advance = [&]() {                          // descriptor of the step after the current one
+        if (redo == 2) return make_int4(-1, 0, 0, 0);
+        if (++chunk == nchunks) {
+            chunk = 0;
+            if (redo == 1) { redo = 2; return make_int4(-1, 0, 0, 0); }
+            u += gridDim.x;
+            if (u >= a.num_units) {
+                if (!a.use_hist) { redo = 2; return make_int4(-1, 0, 0, 0); }
+                redo = 1; u = blockIdx.x; grp = 0;
+            }
+            decode();
+        }
+        return make_int4(chunk, cur_i0, cur_j0, mode_of());
+    };
     auto issue = [&](int st, int ch, int i0, int j0) {
         uint8_t *dst = smem_raw + sm.stage0 + (size_t) st * sm.stage_bytes;
         const char *src = reinterpret_cast<const char *>(a.planes) + (int64_t) ch * a.snp_pad * row_bytes;
@@ -595,9 +666,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
     if (producer) {
         if (u < a.num_units) {
             decode();
-            ctl->meta[0] = make_int4(0, cur_i0, cur_j0, 0);
+            ctl->meta[0] = make_int4(0, cur_i0, cur_j0, mode_of());
             issue(0, 0, cur_i0, cur_j0);
         } else {
+            redo = 2;
             ctl->meta[0] = make_int4(-1, 0, 0, 0);
             mbar_arrive(&ctl->full[0]);
         }
@@ -612,16 +684,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
     for (uint32_t s = 0;; s++) {
         const int st = s & 1;
         if (producer) {
-            int4 next = make_int4(-1, 0, 0, 0);
-            if (u < a.num_units) {
-                // the step after this one
-                if (++chunk == nchunks) {
-                    chunk = 0;
-                    u += gridDim.x;
-                    if (u < a.num_units) decode();
-                }
-                if (u < a.num_units) next = make_int4(chunk, cur_i0, cur_j0, 0);
-            }
+            const int4 next = advance();
             ctl->meta[(s + 1) % 3] = next;
             if (s >= 1) mbar_wait(&ctl->empty[st ^ 1], ((s - 1) >> 1) & 1);   // every warp has read step s - 1
             if (next.x >= 0) issue(st ^ 1, next.x, next.y, next.z);
@@ -631,9 +694,15 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
         mbar_wait(&ctl->full[st], (s >> 1) & 1);
         const int4 meta = ctl->meta[s % 3];
         if (meta.x < 0) break;
-        const int ch = meta.x, i0 = meta.y, j0 = meta.z;
+        const int ch = meta.x, i0 = meta.y, j0 = meta.z, mode = meta.w;
         if (s == 0 && a.stagger) stagger_late_warps(warp, TI, nblocks * 9 * (BW == 3 ? 18 : (BW == 4 ? 24 : 34)));
-        if (ch == 0 && warp == 0 && lane < ctl->fl.F) refresh_threshold(ctl, a, lane);
+        if (ch == 0) {
+            if (a.use_hist) {
+                for (int f = warp; f < ctl->fl.F; f += TI) hist_threshold(ctl, a, f, lane);
+            } else if (warp == 0 && lane < ctl->fl.F) {
+                refresh_threshold(ctl, a, lane);
+            }
+        }
 
         const uint32_t *sbase = reinterpret_cast<const uint32_t *>(smem_raw + sm.stage0 + (size_t) st * sm.stage_bytes);
         const uint32_t *irow = sbase + (size_t) warp * roww;
@@ -716,7 +785,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
                 valid = idx >= a.first && idx < a.last;
             }
             if (__any_sync(0xffffffffu, valid)) {
-                if constexpr (BALANCED) epilogue_balanced<9, SINGLE>(ctl, a, lists, cnts, nwc, nthreads, valid, i, j, -1, lane);
+                if constexpr (BALANCED) epilogue_balanced<9, SINGLE>(ctl, a, lists, cnts, nwc, nthreads, valid, i, j, -1, lane, mode);
                 else epilogue_general<9, SINGLE>(ctl, a, lists, cnts, nwc, nthreads, valid, i, j, -1, lane);
             }
         }
@@ -874,7 +943,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3_kernel(const Search
                 valid = idx >= a.first && idx < a.last;
             }
             if (__any_sync(0xffffffffu, valid)) {
-                if constexpr (BALANCED) epilogue_balanced<27, SINGLE>(ctl, a, lists, cnts, nwc, nthreads, valid, i, j, k, lane);
+                if constexpr (BALANCED) epilogue_balanced<27, SINGLE>(ctl, a, lists, cnts, nwc, nthreads, valid, i, j, k, lane, kModeOffer);
                 else epilogue_general<27, SINGLE>(ctl, a, lists, cnts, nwc, nthreads, valid, i, j, k, lane);
             }
         }

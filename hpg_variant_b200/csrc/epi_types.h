@@ -77,6 +77,12 @@ struct SearchArgs {
     Cand *lists;                // [grid][F][rank]
     int *list_cnt;              // [grid][F]
     long long *gthr;            // [F] global score threshold (lower bound of the N-th best)
+    // score histogram (balanced TRAINING searches with equal folds, order 2): ghist[f][t] counts the pairs seen so far
+    // whose pre-filter score of fold f is t; the N-th best score any CTA can derive from it bounds every list
+    int *ghist;                 // [F][hist_bins]
+    int *ghmax;                 // [F] largest score counted so far (-1: none)
+    int hist_bins;              // A + 1
+    int use_hist;
     int stagger;                // delay the upper half of the warps once by half a unit (HPGV_STAGGER=0 turns it off)
 };
 

@@ -130,6 +130,58 @@ def test_search_balanced_classes_uneven_folds(engine, oracle, order, nv, A, F):
         compare_models(got, want, order)
 
 
+@pytest.mark.parametrize("nv,A,F,rank,subset", [
+    (700, 100, 2, 50, h.SUBSET_TRAINING),     # tri layout, ~480 units: every CTA walks several units (score histogram, re-run of the first unit)
+    (500, 200, 4, 50, h.SUBSET_TRAINING),     # tri layout, four folds
+    (400, 720, 3, 30, h.SUBSET_TRAINING),     # 8-word single-block segments
+    (500, 100, 2, 50, h.SUBSET_TESTING),      # the testing part (no pre-filter, no histogram)
+])
+def test_search_order2_many_units(engine, oracle, nv, A, F, rank, subset):
+    """Searches large enough for the steady state of the persistent kernel: thresholds derived from the global score
+    histogram, lists that stay short, first unit counted first and offered last."""
+    g = synth.make_dataset(nv, A, A, seed=nv + F, missing=0.01, planted=3)
+    fos, _ = h.k_folds(A, A, F, seed=5)
+    engine.load_dataset(g, A, A)
+    engine.set_folds(F, fos)
+    got = engine.search(2, subset, rank)
+    want, _ = oracle.search(g, A, A, 2, fos, subset, rank, threads=16, num_folds=F)
+    compare_models(got, want, 2)
+    # a sub-range that starts and ends inside tiles
+    total = h.num_combinations(nv, 2)
+    lo, hi = total // 5 + 7, total // 3 + 13
+    got = engine.search(2, subset, rank, lo, hi)
+    want, _ = oracle.search(g, A, A, 2, fos, subset, rank, first=lo, last=hi, threads=16, num_folds=F)
+    compare_models(got, want, 2)
+
+
+@pytest.mark.parametrize("nv,A,F", [(3000, 1000, 10), (1500, 2000, 10), (600, 25000, 10)])
+def test_histogram_thresholds_do_not_change_results(engine, monkeypatch, nv, A, F):
+    """c2-, c3- and c5-shaped samples at sizes the CPU oracle cannot reach: the histogram-bounded search returns the
+    bytes of the plain one, whole range and as four sub-ranges merged on the device (size-independent properties)."""
+    import torch
+    rank = 50
+    g = synth.make_dataset(nv, A, A, seed=4242 + nv, missing=0.005, planted=4)
+    fos, _ = h.k_folds(A, A, F, seed=6)
+    engine.load_dataset(g, A, A)
+    engine.set_folds(F, fos)
+    with_hist = engine.search(2, h.SUBSET_TRAINING, rank)
+    total = h.num_combinations(nv, 2)
+    cuts = [0, total // 9, total // 3 + 5, total // 2, total]
+    parts = [engine.search(2, h.SUBSET_TRAINING, rank, cuts[i], cuts[i + 1]) for i in range(4)]
+    lists = torch.from_numpy(np.stack(parts).view(np.uint8)).cuda()
+    out = torch.zeros(F * rank * 40, dtype=torch.uint8, device="cuda")
+    engine.merge_device(2, h.SUBSET_TRAINING, 4, rank, lists.data_ptr(), out.data_ptr())
+    torch.cuda.synchronize()
+    assert out.cpu().numpy().tobytes() == with_hist.tobytes()
+    monkeypatch.setenv("HPGV_HIST", "0")
+    without = engine.search(2, h.SUBSET_TRAINING, rank)
+    assert with_hist.tobytes() == without.tobytes()
+    # every returned model re-evaluates to itself through the per-combination hook
+    ev = engine.eval(2, with_hist["snp"][0, :8, :2].copy(), h.SUBSET_TRAINING)
+    assert np.array_equal(ev["risky_mask"][:, 0], with_hist["risky_mask"][0, :8])
+    assert np.array_equal(ev["conf"][:, 0], with_hist["conf"][0, :8])
+
+
 def test_tri_layout_equals_four_word_layout(engine, monkeypatch):
     """The tri layout (3 words + shared 4-bit tails, 2 POPC per block) and the plain 4-word layout give the same bytes."""
     nv, A, U, F, rank = 150, 1000, 1000, 10, 50
