@@ -552,7 +552,7 @@ static int launch_search(hpgv_epi_ctx *ctx, K kernel, const SearchShape &shape, 
     args.ghmax = ctx->d_hmax.p;
     args.ghist = nullptr;
     if (args.use_hist) {
-        const size_t bins = (size_t) F * args.hist_bins;
+        const size_t bins = (size_t) F * (args.hist_bins + hist_coarse_bins(args.hist_bins));
         CK(ctx->d_hist.reserve(bins));
         CK(cudaMemsetAsync(ctx->d_hist.p, 0, bins * sizeof(int), ctx->stream));
         args.ghist = ctx->d_hist.p;

@@ -44,6 +44,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     while (!mbar_try_wait(bar, parity)) __nanosleep(32);     // leave the issue slots to the warps that still count
 }
+// a 16-byte shared-memory read the compiler may neither hoist nor merge with an earlier read of the same address
+__device__ __forceinline__ int4 ld_volatile_shared_int4(const int4 *p) {
+    int4 v;
+    asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
 // global -> shared, completion signalled on an mbarrier (complete_tx::bytes)
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),

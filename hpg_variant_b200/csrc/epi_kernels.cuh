@@ -333,20 +333,8 @@ __device__ __forceinline__ int dp4a_us(uint32_t a8x4, uint32_t b8x4, int c) {
 // with D_c = totA_c - totU_c and d_cf = inA_cf - inU_cf: one IDP (dot product with +-1 bytes) and one VIMNMX.RELU per
 // cell and fold, no unpacking, no risk mask.  Returns whether any fold of this thread's tuple reaches the fold's bound
 // ctl->tq; only then is the exact epilogue (masks, TP/FP, BA, list offer) run.  A stale (lower) bound only costs time.
-//
-// mode (per step, from the producer): bit 0 = count the scores that reach the bound into the global histogram (every
-// score when bit 1 is clear), bit 1 = candidates are offered to the lists.  See hist_threshold().
-constexpr int kModeCount = 1, kModeOffer = 2;
-
-__device__ __forceinline__ void hist_count(const SearchArgs &a, int f, int t, bool on) {
-    if (on) atomicAdd(a.ghist + (size_t) f * a.hist_bins + t, 1);
-    const int m = __reduce_max_sync(0xffffffffu, on ? t : -1);
-    if ((threadIdx.x & 31) == 0 && m >= 0 && m > __ldcg(a.ghmax + f)) atomicMax(a.ghmax + f, m);
-}
-
 template <int NCELLS, bool U8>
-__device__ __forceinline__ bool balanced_prefilter(const SearchCtl *ctl, const SearchArgs &a, const uint32_t *cnts, int nwc, bool valid,
-                                                   int mode) {
+__device__ __forceinline__ bool balanced_prefilter(const SearchCtl *ctl, const uint32_t *cnts, int nwc) {
     int D[NCELLS];
 #pragma unroll
     for (int c = 0; c < NCELLS; c++) D[c] = 0;
@@ -368,14 +356,7 @@ __device__ __forceinline__ bool balanced_prefilter(const SearchCtl *ctl, const S
                 t0 += max(dp4a_us(w, 0x000100FFu, D[c]), 0);
                 t1 += max(dp4a_us(w, 0x0100FF00u, D[c]), 0);
             }
-            const bool p0 = t0 >= tq[2 * k], p1 = t1 >= tq[2 * k + 1];
-            pass |= p0 | p1;
-            if (mode & kModeCount) {
-                const bool all = !(mode & kModeOffer);
-                const bool c0 = valid && (p0 || all), c1 = valid && (p1 || all) && 2 * k + 1 < ctl->fl.F;
-                if (__any_sync(0xffffffffu, c0)) hist_count(a, 2 * k, t0, c0);
-                if (__any_sync(0xffffffffu, c1)) hist_count(a, 2 * k + 1, t1, c1);
-            }
+            pass |= (t0 >= tq[2 * k]) | (t1 >= tq[2 * k + 1]);
         } else {                                              // w = A_k | U_k << 16
             int t = 0;
 #pragma unroll
@@ -383,15 +364,51 @@ __device__ __forceinline__ bool balanced_prefilter(const SearchCtl *ctl, const S
                 const uint32_t w = cnts[k * NCELLS + c];
                 t += max(dp2a_lo_us(w, 0x000001FFu, D[c]), 0);
             }
-            const bool p = t >= tq[k];
-            pass |= p;
-            if (mode & kModeCount) {
-                const bool c = valid && (p || !(mode & kModeOffer));
-                if (__any_sync(0xffffffffu, c)) hist_count(a, k, t, c);
-            }
+            pass |= t >= tq[k];
         }
     }
     return pass;
+}
+
+// mode of a step (from the producer): bit 0 = count scores into the global histogram -- those that reach the bound,
+// or every score when bit 1 is clear; bit 1 = candidates are offered to the lists.  See hist_threshold().
+constexpr int kModeCount = 1, kModeOffer = 2;
+
+// The pre-filter scores of this thread's tuple once more, this time counted into the global histogram.  Runs for the
+// whole first unit of a CTA (all = true) and afterwards only for warps that hold a candidate: kept out of line so that
+// it costs the common path no registers.
+template <int NCELLS, bool U8>
+__device__ __noinline__ void hist_count_tuple(const SearchCtl *ctl, int *ghist, int *ghmax, int hist_bins, const uint32_t *cnts, int nwc,
+                                              bool valid, bool all) {
+    int D[NCELLS];
+#pragma unroll
+    for (int c = 0; c < NCELLS; c++) D[c] = 0;
+    for (int k = 0; k < nwc; k++) {
+#pragma unroll
+        for (int c = 0; c < NCELLS; c++) {
+            const uint32_t w = cnts[k * NCELLS + c];
+            D[c] = U8 ? dp4a_us(w, 0xFFFF0101u, D[c]) : dp2a_lo_us(w, 0x0000FF01u, D[c]);
+        }
+    }
+    const volatile int *tq = ctl->tq;
+    const int F = ctl->fl.F;
+    for (int f = 0; f < F; f++) {
+        const int k = U8 ? (f >> 1) : f;
+        const uint32_t sel = U8 ? ((f & 1) ? 0x0100FF00u : 0x000100FFu) : 0x000001FFu;
+        int t = 0;
+#pragma unroll
+        for (int c = 0; c < NCELLS; c++) {
+            const uint32_t w = cnts[k * NCELLS + c];
+            t += max(U8 ? dp4a_us(w, sel, D[c]) : dp2a_lo_us(w, sel, D[c]), 0);
+        }
+        const bool on = valid && (all || t >= tq[f]);
+        if (on) {
+            atomicAdd(ghist + (size_t) f * hist_bins + t, 1);
+            atomicAdd(ghist + (size_t) F * hist_bins + (size_t) f * hist_coarse_bins(hist_bins) + (t >> 5), 1);
+        }
+        const int m = __reduce_max_sync(0xffffffffu, on ? t : -1);
+        if ((threadIdx.x & 31) == 0 && m >= 0 && m > __ldcg(ghmax + f)) atomicMax(ghmax + f, m);
+    }
 }
 
 // Fast version for balanced data sets (A == U <= 65535): every count pair travels as
@@ -403,9 +420,13 @@ __device__ __forceinline__ void epilogue_balanced_t(SearchCtl *ctl, const Search
     const int nfolds = ctl->fl.F;
     if constexpr (TRAINING) {
         if (ctl->fl.eqfolds) {
-            const bool pass = balanced_prefilter<NCELLS, U8>(ctl, a, cnts, nwc, valid, mode);
-            if (!(mode & kModeOffer)) return;
+            if (mode == kModeCount) {                          // the CTA's first unit: counted now, offered at the end
+                hist_count_tuple<NCELLS, U8>(ctl, a.ghist, a.ghmax, a.hist_bins, cnts, nwc, valid, true);
+                return;
+            }
+            const bool pass = balanced_prefilter<NCELLS, U8>(ctl, cnts, nwc);
             if (!__any_sync(0xffffffffu, pass && valid)) return;
+            if (mode & kModeCount) hist_count_tuple<NCELLS, U8>(ctl, a.ghist, a.ghmax, a.hist_bins, cnts, nwc, valid, false);
         }
     }
     uint32_t tot[NCELLS];                     // total cases | total controls << 16
@@ -542,26 +563,45 @@ __device__ __forceinline__ void refresh_threshold(SearchCtl *ctl, const SearchAr
     }
 }
 
-// Once per unit and fold (one warp each): the largest score T such that at least N pairs counted in the global
-// histogram reach it.  Those pairs are distinct members of this search's range, so no pair below T can be among the
-// N best of the fold: T becomes the bound of the CTA's pre-filter and list.  A stale histogram only gives a lower T.
-__device__ __forceinline__ void hist_threshold(SearchCtl *ctl, const SearchArgs &a, int f, int lane) {
-    const int hmax = __ldcg(a.ghmax + f);
-    const int cur = *reinterpret_cast<volatile int *>(&ctl->tq[f]);
-    const int lo = max(cur, 0);                      // scores below the current bound are not counted any more
-    if (hmax < lo) return;
-    const int *h = a.ghist + (size_t) f * a.hist_bins;
-    int cum = 0, T = INT_MIN;
-    for (int base = hmax; base >= lo; base -= 32) {
-        const int t = base - lane;                   // lane 0 reads the highest score of the window
-        int incl = (t >= lo) ? __ldcg(h + t) : 0;
+// One warp, one fold: the largest score T such that at least N pairs counted in the global histogram reach it.
+// Those pairs are distinct members of this search's range, so no pair below T can be among the N best of the fold: T
+// becomes the bound of the CTA's pre-filter and list.  Counts are only ever too low (stale reads, pairs below some
+// CTA's bound are not counted), which can only lower T.  Two levels: coarse bins of 32 scores are scanned from the
+// top, 32 at a time, then the 32 fine bins of the coarse bin that holds the N-th pair.
+__device__ __forceinline__ int warp_inclusive_scan(int v, int lane) {
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += n;
+    for (int d = 1; d < 32; d <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += n;
+    }
+    return v;
+}
+__device__ __noinline__ void hist_threshold(SearchCtl *ctl, const int *ghist, const int *ghmax, int hist_bins, int rank, int f, int lane) {
+    const int hmax = __ldcg(ghmax + f);
+    const int cur = *reinterpret_cast<volatile int *>(&ctl->tq[f]);
+    if (hmax < 0 || hmax < cur) return;
+    const int F = ctl->fl.F, cbins = hist_coarse_bins(hist_bins);
+    const int *h = ghist + (size_t) f * hist_bins;
+    const int *hc = ghist + (size_t) F * hist_bins + (size_t) f * cbins;
+    const int cfloor = max(cur, 0) >> 5;             // below this coarse bin no better bound can come out
+    int cum = 0, T = INT_MIN;
+    for (int cbase = hmax >> 5; cbase >= cfloor; cbase -= 32) {
+        const int cbin = cbase - lane;               // lane 0 reads the highest bin of the window
+        const int v = cbin >= 0 ? __ldcg(hc + cbin) : 0;
+        const int incl = warp_inclusive_scan(v, lane);
+        const unsigned hit = __ballot_sync(0xffffffffu, cum + incl >= rank);
+        if (hit) {
+            const int l = __ffs(hit) - 1;
+            const int cstar = cbase - l;
+            const int above = cum + __shfl_sync(0xffffffffu, incl, l) - __shfl_sync(0xffffffffu, v, l);
+            const int t = cstar * 32 + 31 - lane;
+            const int fv = t < hist_bins ? __ldcg(h + t) : 0;
+            const int fincl = warp_inclusive_scan(fv, lane);
+            const unsigned fhit = __ballot_sync(0xffffffffu, above + fincl >= rank);
+            // the fine counts may lag the coarse one: the bin's lowest score is then the (valid) answer
+            T = fhit ? cstar * 32 + 31 - (__ffs(fhit) - 1) : cstar * 32;
+            break;
         }
-        const unsigned hit = __ballot_sync(0xffffffffu, cum + incl >= a.rank);
-        if (hit) { T = base - (__ffs(hit) - 1); break; }
         cum += __shfl_sync(0xffffffffu, incl, 31);
     }
     if (lane == 0 && T != INT_MIN && T > cur) {
@@ -694,11 +734,15 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
         mbar_wait(&ctl->full[st], (s >> 1) & 1);
         const int4 meta = ctl->meta[s % 3];
         if (meta.x < 0) break;
-        const int ch = meta.x, i0 = meta.y, j0 = meta.z, mode = meta.w;
+        const int ch = meta.x;
         if (s == 0 && a.stagger) stagger_late_warps(warp, TI, nblocks * 9 * (BW == 3 ? 18 : (BW == 4 ? 24 : 34)));
         if (ch == 0) {
             if (a.use_hist) {
-                for (int f = warp; f < ctl->fl.F; f += TI) hist_threshold(ctl, a, f, lane);
+                // every unit at first, then ever more rarely: the bound rises with the logarithm of the pairs seen, and
+                // the warps that pay the L2 round trips are late at the next hand-off of a stage
+                const uint32_t n = s / (uint32_t) nchunks;
+                if (n >= 1 && (n < 8 || (n < 64 ? (n & 7) == 0 : (n & 31) == 0)))
+                    for (int f = warp; f < ctl->fl.F; f += TI) hist_threshold(ctl, a.ghist, a.ghmax, a.hist_bins, a.rank, f, lane);
             } else if (warp == 0 && lane < ctl->fl.F) {
                 refresh_threshold(ctl, a, lane);
             }
@@ -775,9 +819,13 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
         }
 
         __syncwarp();
+        // the step descriptor is read again here (its slot is rewritten two steps later, which needs this warp's
+        // arrival below) so that the tile origins hold no registers during the counting phase
+        const int4 meta2 = ld_volatile_shared_int4(&ctl->meta[s % 3]);
         if (lane == 0) mbar_arrive(&ctl->empty[st]);        // this warp is done with the stage
 
-        if (ch == nchunks - 1) {
+        if (meta2.x == nchunks - 1) {
+            const int i0 = meta2.y, j0 = meta2.z, mode = meta2.w;
             const int i = i0 + warp, j = j0 + lane;
             bool valid = (i < j) && (j < a.nv);
             if (valid) {
@@ -875,7 +923,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3_kernel(const Search
         mbar_wait(&ctl->full[st], (s >> 1) & 1);
         const int4 meta = ctl->meta[s % 3];
         if (meta.x < 0) break;
-        const int ch = meta.x, i = meta.y, j0 = meta.z, k0 = meta.w;
+        const int ch = meta.x;
         if (s == 0 && a.stagger) stagger_late_warps(warp, TJ, nblocks * 27 * (BW == 4 ? 24 : 34));
         if (ch == 0 && warp == 0 && lane < ctl->fl.F) refresh_threshold(ctl, a, lane);
 
@@ -933,9 +981,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3_kernel(const Search
         }
 
         __syncwarp();
+        const int4 meta2 = ld_volatile_shared_int4(&ctl->meta[s % 3]);      // see search2_kernel
         if (lane == 0) mbar_arrive(&ctl->empty[st]);
 
-        if (ch == nchunks - 1) {
+        if (meta2.x == nchunks - 1) {
+            const int i = meta2.y, j0 = meta2.z, k0 = meta2.w;
             const int j = j0 + warp, k = k0 + lane;
             bool valid = (i < j) && (j < k) && (k < a.nv);
             if (valid) {

@@ -48,6 +48,11 @@ struct FoldLayout {
     int u_in[kMaxFolds];
 };
 
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline int hist_coarse_bins(int hist_bins) { return (hist_bins + 31) / 32; }
+
 // Candidate / ranked entry as kept on the device (32 bytes, two 16-byte words).
 struct __attribute__((aligned(16))) Cand {
     double ba;      // balanced accuracy; -inf encodes NaN (ranks last)
@@ -79,7 +84,7 @@ struct SearchArgs {
     long long *gthr;            // [F] global score threshold (lower bound of the N-th best)
     // score histogram (balanced TRAINING searches with equal folds, order 2): ghist[f][t] counts the pairs seen so far
     // whose pre-filter score of fold f is t; the N-th best score any CTA can derive from it bounds every list
-    int *ghist;                 // [F][hist_bins]
+    int *ghist;                 // [F][hist_bins] fine bins, then [F][hist_coarse_bins(hist_bins)] bins of 32 scores
     int *ghmax;                 // [F] largest score counted so far (-1: none)
     int hist_bins;              // A + 1
     int use_hist;
