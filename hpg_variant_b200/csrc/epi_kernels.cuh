@@ -401,13 +401,20 @@ __device__ __noinline__ void hist_count_tuple(const SearchCtl *ctl, int *ghist, 
             const uint32_t w = cnts[k * NCELLS + c];
             t += max(U8 ? dp4a_us(w, sel, D[c]) : dp2a_lo_us(w, sel, D[c]), 0);
         }
-        const bool on = valid && (all || t >= tq[f]);
+        bool on = valid && (all || t >= tq[f]);
+        const int m = __reduce_max_sync(0xffffffffu, on ? t : -1);
+        if (m < 0) continue;
+        if (all) {
+            // first unit: one pair per warp and fold, the best one -- the N best of the ~2400 warps' best pairs bound the
+            // N-th best of all their pairs almost as well, at 1/32 of the atomics on a handful of hot addresses
+            const unsigned best = __ballot_sync(0xffffffffu, on && t == m);
+            on = (threadIdx.x & 31) == (unsigned) (__ffs(best) - 1);
+        }
         if (on) {
             atomicAdd(ghist + (size_t) f * hist_bins + t, 1);
             atomicAdd(ghist + (size_t) F * hist_bins + (size_t) f * hist_coarse_bins(hist_bins) + (t >> 5), 1);
+            if (t == m) atomicMax(ghmax + f, m);     // fire and forget; several lanes at most when scores tie
         }
-        const int m = __reduce_max_sync(0xffffffffu, on ? t : -1);
-        if ((threadIdx.x & 31) == 0 && m >= 0 && m > __ldcg(ghmax + f)) atomicMax(ghmax + f, m);
     }
 }
 
