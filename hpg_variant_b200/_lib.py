@@ -36,7 +36,7 @@ SYMBOLS = [
     "hpgv_epi_load_dataset_host", "hpgv_epi_load_dataset_device", "hpgv_epi_load_dataset_file", "hpgv_epi_dataset_dims",
     "hpgv_epi_set_folds", "hpgv_epi_k_folds", "hpgv_epi_search", "hpgv_epi_search_device", "hpgv_epi_merge_device",
     "hpgv_epi_num_combinations", "hpgv_epi_eval", "hpgv_epi_unpack_masks", "hpgv_epi_run_host", "hpgv_epi_layout",
-    "hpgv_epi_pipe_peak", "hpgv_epi_last_search_ms",
+    "hpgv_epi_pipe_peak", "hpgv_epi_last_search_ms", "hpgv_epi_search_times",
 ]
 
 
@@ -74,6 +74,7 @@ def load():
     lib.hpgv_epi_run_host.argtypes = [vp, vp, i64, i32, i32, i32, vp, i32, i32, i32, u64, u64, vp]
     lib.hpgv_epi_layout.argtypes = [vp, C.POINTER(Layout)]
     lib.hpgv_epi_last_search_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i32)]
+    lib.hpgv_epi_search_times.argtypes = [vp, i32, C.POINTER(C.c_float)]
     lib.hpgv_epi_pipe_peak.argtypes = [vp, i32, i32, C.POINTER(C.c_double)]
     _lib = lib
     return lib

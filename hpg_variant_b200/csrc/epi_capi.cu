@@ -87,11 +87,18 @@ struct hpgv_epi_ctx {
     uint64_t wl_first = 0, wl_last = 0;
     int64_t wl_nv = -1;
     int wl_it0 = 0, wl_nit = 0;
+    int wl_edge_lo = 0, wl_edge_hi = 0;
     int64_t wl_units = 0;
     // device-side timing of the dominant kernel (bench.py's roofline): events around every search launch
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool ev_valid = false;
+    static constexpr int kEvRing = 32;
+    cudaEvent_t ev0[kEvRing] = {}, ev1[kEvRing] = {};
+    int64_t ev_count = 0;                 // search launches so far; launch k uses slot k % kEvRing
     int last_grid = 0;
+    // pinned staging of the fold layout, permutation and block descriptors (set_folds does not synchronise the stream)
+    uint8_t *h_stage = nullptr;
+    size_t h_stage_cap = 0;
+    cudaEvent_t ev_stage = nullptr;
+    bool stage_busy = false;
 };
 
 #define CK(call)                                                                                   \
@@ -153,8 +160,8 @@ extern "C" int hpgv_epi_create(int device, hpgv_epi_ctx **out) {
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
     ctx->max_smem_optin = (int) prop.sharedMemPerBlockOptin;
-    cudaEventCreate(&ctx->ev0);
-    cudaEventCreate(&ctx->ev1);
+    for (int k = 0; k < hpgv_epi_ctx::kEvRing; k++) { cudaEventCreate(&ctx->ev0[k]); cudaEventCreate(&ctx->ev1[k]); }
+    cudaEventCreateWithFlags(&ctx->ev_stage, cudaEventDisableTiming);
     *out = ctx;
     return HPGV_OK;
 }
@@ -165,8 +172,9 @@ extern "C" void hpgv_epi_destroy(hpgv_epi_ctx *ctx) {
     ctx->raw_owned.release(); ctx->d_fl.release(); ctx->d_perm.release(); ctx->d_blk.release(); ctx->d_planes.release();
     ctx->d_lists.release(); ctx->d_list_cnt.release(); ctx->d_gthr.release(); ctx->d_hist.release(); ctx->d_hmax.release();
     ctx->d_prefix.release(); ctx->d_jt0.release(); ctx->d_out.release(); ctx->d_merge_in.release();
-    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (int k = 0; k < hpgv_epi_ctx::kEvRing; k++) { if (ctx->ev0[k]) cudaEventDestroy(ctx->ev0[k]); if (ctx->ev1[k]) cudaEventDestroy(ctx->ev1[k]); }
+    if (ctx->ev_stage) cudaEventDestroy(ctx->ev_stage);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     delete ctx;
 }
 
@@ -360,24 +368,54 @@ static int apply_folds(hpgv_epi_ctx *ctx, int F, const int32_t *fold_of_sample, 
     ctx->snp_pad = ((ctx->nv + kTileJ - 1) / kTileJ) * kTileJ + kTileJ;
     ctx->plane_words = (size_t) fl.nchunks * (size_t) ctx->snp_pad * fl.row_words;
 
+    // a growing device buffer is freed and re-allocated: nothing enqueued earlier may still use it
+    if (ctx->perm.size() > ctx->d_perm.cap || ctx->blk.size() > ctx->d_blk.cap || ctx->plane_words > ctx->d_planes.cap || ctx->d_fl.cap < 1)
+        CK(cudaStreamSynchronize(ctx->stream));
     CK(ctx->d_fl.reserve(1));
     CK(ctx->d_perm.reserve(ctx->perm.size()));
     CK(ctx->d_blk.reserve(ctx->blk.size()));
     CK(ctx->d_planes.reserve(ctx->plane_words));
-    CK(cudaMemcpyAsync(ctx->d_fl.p, &ctx->fl, sizeof(FoldLayout), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_perm.p, ctx->perm.data(), ctx->perm.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_blk.p, ctx->blk.data(), ctx->blk.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        // layout, permutation and block descriptors go up from pinned staging memory: truly asynchronous copies, the
+        // staging buffer is reused once the copies of the previous call have completed
+        const size_t o_perm = align_up(sizeof(FoldLayout), 16), o_blk = o_perm + align_up(ctx->perm.size() * sizeof(int32_t), 16);
+        const size_t need = o_blk + align_up(ctx->blk.size() * sizeof(uint16_t), 16);
+        if (ctx->stage_busy) CK(cudaEventSynchronize(ctx->ev_stage));
+        if (need > ctx->h_stage_cap) {
+            if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+            ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
+            CK(cudaMallocHost(reinterpret_cast<void **>(&ctx->h_stage), need));
+            ctx->h_stage_cap = need;
+        }
+        memcpy(ctx->h_stage, &ctx->fl, sizeof(FoldLayout));
+        memcpy(ctx->h_stage + o_perm, ctx->perm.data(), ctx->perm.size() * sizeof(int32_t));
+        memcpy(ctx->h_stage + o_blk, ctx->blk.data(), ctx->blk.size() * sizeof(uint16_t));
+        CK(cudaMemcpyAsync(ctx->d_fl.p, ctx->h_stage, sizeof(FoldLayout), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_perm.p, ctx->h_stage + o_perm, ctx->perm.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_blk.p, ctx->h_stage + o_blk, ctx->blk.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->ev_stage, ctx->stream));
+        ctx->stage_busy = true;
+    }
     CK(cudaMemsetAsync(ctx->d_planes.p, 0, ctx->plane_words * sizeof(uint32_t), ctx->stream));
 
-    const int64_t warps = ctx->nv * (int64_t) nb * fl.bw;
     const int threads = 256;
-    const int64_t blocks = (warps * 32 + threads - 1) / threads;
-    if (blocks > INT32_MAX) FAIL(HPGV_E_UNSUPPORTED, "dataset too large for the packer grid");
-    pack_planes_kernel<<<(unsigned) blocks, threads, 0, ctx->stream>>>(ctx->d_raw, ctx->nv, S, ctx->d_perm.p, ctx->d_fl.p, ctx->snp_pad, ctx->d_planes.p);
+    const PackSmem pm = pack_smem_map(ctx->npos, S, fl);
+    const char *old_packer = getenv("HPGV_PACK_WARP");          // A/B switch: the one-warp-per-word packer
+    if (pm.total <= 56 * 1024 && !(old_packer && old_packer[0] == '1')) {
+        // several CTAs per SM hide the latency of the row loads; each walks SNPs blockIdx.x, + gridDim.x, ...
+        if (pm.total > 48 * 1024) CK(cudaFuncSetAttribute(pack_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pm.total));
+        const int per_sm = (int) std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / pm.total));
+        const int64_t grid = std::min<int64_t>((ctx->nv + kPackRows - 1) / kPackRows, (int64_t) ctx->num_sms * per_sm);
+        pack_rows_kernel<<<(unsigned) grid, threads, pm.total, ctx->stream>>>(ctx->d_raw, ctx->nv, S, ctx->d_perm.p, ctx->d_fl.p, ctx->snp_pad,
+                                                                              ctx->npos, ctx->d_planes.p);
+    } else {
+        const int64_t warps = ctx->nv * (int64_t) nb * fl.bw;
+        const int64_t blocks = (warps * 32 + threads - 1) / threads;
+        if (blocks > INT32_MAX) FAIL(HPGV_E_UNSUPPORTED, "dataset too large for the packer grid");
+        pack_planes_kernel<<<(unsigned) blocks, threads, 0, ctx->stream>>>(ctx->d_raw, ctx->nv, S, ctx->d_perm.p, ctx->d_fl.p, ctx->snp_pad, ctx->d_planes.p);
+    }
     CK(cudaGetLastError());
     ctx->launches++;
-    // perm/blk host vectors are read by the async copies above
-    CK(cudaStreamSynchronize(ctx->stream));
     ctx->folds_set = true;
     return HPGV_OK;
 }
@@ -469,11 +507,13 @@ static int build_worklist(hpgv_epi_ctx *ctx, int order, int ti, uint64_t first, 
     std::vector<int32_t> jt0;
     int it0 = 0;
     int64_t units = 0;
+    int64_t edge_lo = 0, edge_hi = 0;
     if (first < last) {
         if (order == 2) {
             int64_t i_first, j_first, i_last, j_last;
             unrank_pair((uint64_t) nv, first, &i_first, &j_first);
             unrank_pair((uint64_t) nv, last - 1, &i_last, &j_last);
+            edge_lo = i_first; edge_hi = i_last;
             it0 = (int) (i_first / ti);
             const int it1 = (int) (i_last / ti);
             for (int t = it0; t <= it1; t++) {
@@ -492,6 +532,7 @@ static int build_worklist(hpgv_epi_ctx *ctx, int order, int ti, uint64_t first, 
             const int tj = ti;
             const int64_t i_first = unrank_triple_first((uint64_t) nv, first);
             const int64_t i_last = unrank_triple_first((uint64_t) nv, last - 1);
+            edge_lo = i_first; edge_hi = i_last;
             it0 = (int) i_first;
             for (int64_t i = i_first; i <= i_last; i++) {
                 prefix.push_back(units);
@@ -509,6 +550,7 @@ static int build_worklist(hpgv_epi_ctx *ctx, int order, int ti, uint64_t first, 
     CK(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
     ctx->wl_nv = nv; ctx->wl_order = order; ctx->wl_ti = ti; ctx->wl_first = first; ctx->wl_last = last;
     ctx->wl_it0 = it0; ctx->wl_nit = (int) prefix.size(); ctx->wl_units = units;
+    ctx->wl_edge_lo = (int) edge_lo; ctx->wl_edge_hi = (int) edge_hi;
     return HPGV_OK;
 }
 
@@ -560,18 +602,19 @@ static int launch_search(hpgv_epi_ctx *ctx, K kernel, const SearchShape &shape, 
     args.lists_in_smem = shape.lists_in_smem ? 1 : 0;
     reset_search_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_gthr.p, ctx->d_hmax.p);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    const int slot = (int) (ctx->ev_count % hpgv_epi_ctx::kEvRing);
+    CK(cudaEventRecord(ctx->ev0[slot], ctx->stream));
     kernel<<<(unsigned) grid, shape.nthreads, shape.smem, ctx->stream>>>(args);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    ctx->ev_valid = true;
+    CK(cudaEventRecord(ctx->ev1[slot], ctx->stream));
+    ctx->ev_count++;
     ctx->last_grid = (int) grid;
     ctx->launches += 2;
     return (int) grid;
 }
 
 static int launch_merge(hpgv_epi_ctx *ctx, const MergeArgs &m) {
-    const size_t smem = (size_t) m.rank_out * 20 + 16;
+    const size_t smem = merge_smem_bytes(m.rank_out);
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     merge_kernel<<<m.F, kMergeThreads, smem, ctx->stream>>>(m);
     CK(cudaGetLastError());
@@ -629,6 +672,8 @@ static int do_search(hpgv_epi_ctx *ctx, int order, int eval_subset, int rank, ui
     args.it0 = ctx->wl_it0;
     args.n_it = ctx->wl_nit;
     args.num_units = ctx->wl_units;
+    args.edge_lo = ctx->wl_edge_lo;
+    args.edge_hi = ctx->wl_edge_hi;
 
     // the packed-pair epilogue needs A == U (r = 1: the float32 rule is exact) and 16-bit class sizes
     const bool balanced = fl.balanced && fl.A <= 65535;
@@ -787,11 +832,23 @@ extern "C" int hpgv_epi_run_host(hpgv_epi_ctx *ctx, const uint8_t *genotypes, in
 
 extern "C" int hpgv_epi_last_search_ms(hpgv_epi_ctx *ctx, float *ms, int *grid) {
     if (!ctx || !ms) return HPGV_E_ARG;
-    if (!ctx->ev_valid) FAIL(HPGV_E_STATE, "no search has been launched yet");
-    CK(cudaEventSynchronize(ctx->ev1));
-    CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    if (ctx->ev_count == 0) FAIL(HPGV_E_STATE, "no search has been launched yet");
+    const int slot = (int) ((ctx->ev_count - 1) % hpgv_epi_ctx::kEvRing);
+    CK(cudaEventSynchronize(ctx->ev1[slot]));
+    CK(cudaEventElapsedTime(ms, ctx->ev0[slot], ctx->ev1[slot]));
     if (grid) *grid = ctx->last_grid;
     return HPGV_OK;
+}
+
+extern "C" int hpgv_epi_search_times(hpgv_epi_ctx *ctx, int n, float *ms) {
+    if (!ctx || !ms || n < 0) return HPGV_E_ARG;
+    n = (int) std::min<int64_t>(std::min<int64_t>(n, hpgv_epi_ctx::kEvRing), ctx->ev_count);
+    for (int k = 0; k < n; k++) {
+        const int slot = (int) ((ctx->ev_count - n + k) % hpgv_epi_ctx::kEvRing);
+        CK(cudaEventSynchronize(ctx->ev1[slot]));
+        CK(cudaEventElapsedTime(ms + k, ctx->ev0[slot], ctx->ev1[slot]));
+    }
+    return n;
 }
 
 extern "C" int hpgv_epi_layout(const hpgv_epi_ctx *ctx, hpgv_epi_layout_t *out) {

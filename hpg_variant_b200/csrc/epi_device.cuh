@@ -40,9 +40,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// the waiting warp is suspended by the hardware (up to the hinted time) instead of spinning through issue slots
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    while (!mbar_try_wait(bar, parity)) __nanosleep(32);     // leave the issue slots to the warps that still count
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "HPGV_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra HPGV_DONE;\n"
+        "bra HPGV_WAIT;\n"
+        "HPGV_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+        : "memory");
 }
 // a 16-byte shared-memory read the compiler may neither hoist nor merge with an earlier read of the same address
 __device__ __forceinline__ int4 ld_volatile_shared_int4(const int4 *p) {

@@ -63,6 +63,90 @@ __global__ void pack_planes_kernel(const uint8_t *__restrict__ raw, int64_t nv, 
     }
 }
 
+// The same through shared memory, for sample axes whose permutation fits there (all but the largest cohorts): a CTA
+// takes one SNP at a time, reads its bytes with coalesced 16-byte loads, gathers them through the permutation kept in
+// shared memory, assembles the packed row(s) there and writes them out coalesced.  HBM-bound by design: nsamples bytes
+// in, 3 x nsamples / 8 (+ padding) out per SNP.
+struct PackSmem {
+    size_t perm, ofs, row, out, total;
+};
+constexpr int kPackRows = 4;      // SNPs a CTA packs per iteration (their rows are contiguous on both sides)
+__host__ __device__ inline PackSmem pack_smem_map(int64_t npos, int64_t nsamples, const FoldLayout &fl) {
+    PackSmem m;
+    m.perm = 0;
+    m.ofs = (size_t) npos * 4;                                           // one int per logical word (npos / 32 of them)
+    m.row = m.ofs + (((size_t) (npos / 32) * 4 + 15) / 16) * 16;
+    m.out = m.row + (((size_t) nsamples * kPackRows + 15) / 16 + 1) * 16;   // + 16: staged at the global misalignment
+    m.total = m.out + (size_t) kPackRows * fl.nchunks * fl.row_words * 4;
+    return m;
+}
+__global__ void __launch_bounds__(256) pack_rows_kernel(const uint8_t *__restrict__ raw, int64_t nv, int64_t nsamples,
+                                                        const int32_t *__restrict__ perm, const FoldLayout *__restrict__ flp,
+                                                        int64_t snp_pad, int64_t npos, uint32_t *__restrict__ planes) {
+    extern __shared__ __align__(16) uint8_t psm[];
+    const PackSmem m = pack_smem_map(npos, nsamples, *flp);
+    int32_t *perm_s = reinterpret_cast<int32_t *>(psm + m.perm);
+    int32_t *ofs_s = reinterpret_cast<int32_t *>(psm + m.ofs);
+    uint8_t *row_s = psm + m.row;
+    uint32_t *out_s = reinterpret_cast<uint32_t *>(psm + m.out);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int bw = flp->bw, lbw = bw == 8 ? 3 : 2, nwords = flp->nblocks * bw, tri = flp->tri, cb = flp->cb, nblocks = flp->nblocks;
+    const int row_words = flp->row_words, nchunks = flp->nchunks;
+    const int out_words = nchunks * row_words;                           // per SNP, chunk-major
+    const int gstride = tri ? 12 : bw;                                   // words between the planes of one block
+    for (int64_t x = tid; x < npos; x += blockDim.x) perm_s[x] = perm[x];
+    // where logical word wb of plane 0 goes inside the staged output of one SNP; tri tails: -(offset + 1) | shift << 24
+    for (int wb = tid; wb < nwords; wb += blockDim.x) {
+        const int b = wb >> lbw, w = wb & (bw - 1);
+        int o;
+        if (tri) o = w < 3 ? tri_word_off(b, 0, w) : -((tri_tail_off(nblocks, b, 0) + 1) | (tri_tail_shift(b) << 24));
+        else o = (b / cb) * row_words + ((b % cb) * 3) * bw + w;
+        ofs_s[wb] = o;
+    }
+    for (int64_t snp0 = (int64_t) blockIdx.x * kPackRows; snp0 < nv; snp0 += (int64_t) gridDim.x * kPackRows) {
+        const int nr = (int) min((int64_t) kPackRows, nv - snp0);
+        // stage the rows: 16-byte loads from the aligned address at or below the first byte
+        const uint8_t *src = raw + snp0 * nsamples;
+        const int64_t nbytes = (int64_t) nr * nsamples;
+        const int mis = (int) (reinterpret_cast<uintptr_t>(src) & 15);
+        // a 16-byte group may reach outside the matrix at its two ends: those rows are read bytewise
+        if ((snp0 + nr < nv || ((nbytes + mis) & 15) == 0) && (snp0 > 0 || mis == 0)) {
+            const uint4 *src16 = reinterpret_cast<const uint4 *>(src - mis);
+            const int n16 = (int) ((nbytes + mis + 15) / 16);
+            for (int x = tid; x < n16; x += blockDim.x) reinterpret_cast<uint4 *>(row_s)[x] = __ldg(src16 + x);
+        } else {
+            for (int64_t x = tid; x < nbytes; x += blockDim.x) row_s[mis + x] = src[x];
+        }
+        for (int x = tid; x < nr * out_words; x += blockDim.x) out_s[x] = 0;
+        __syncthreads();
+        for (int r = 0; r < nr; r++)
+        for (int wb = warp; wb < nwords; wb += nwarps) {
+            const int32_t col = perm_s[wb * 32 + lane];
+            const uint32_t g = col >= 0 ? row_s[mis + r * nsamples + col] : 255u;
+            const uint32_t m0 = __ballot_sync(0xffffffffu, g == 0);
+            const uint32_t m1 = __ballot_sync(0xffffffffu, g == 1);
+            const uint32_t m2 = __ballot_sync(0xffffffffu, g == 2);
+            const uint32_t mine = lane == 0 ? m0 : (lane == 1 ? m1 : m2);
+            if (lane < 3) {
+                const int o = ofs_s[wb];
+                uint32_t *dst = out_s + r * out_words;
+                if (o >= 0) dst[o + lane * gstride] = mine;
+                else if (mine & 0xFu) atomicOr(dst + ((-o) & 0xFFFFFF) - 1 + lane, (mine & 0xFu) << ((-o) >> 24));
+            }
+        }
+        __syncthreads();
+        // chunk ch of the nr SNPs is one contiguous run of nr * row_words words in global memory
+        for (int ch = 0; ch < nchunks; ch++) {
+            uint4 *dst = reinterpret_cast<uint4 *>(planes + ((int64_t) ch * snp_pad + snp0) * row_words);
+            for (int x = tid; x < nr * (row_words / 4); x += blockDim.x) {
+                const int r = x / (row_words / 4), q = x - r * (row_words / 4);
+                dst[x] = reinterpret_cast<const uint4 *>(out_s + r * out_words + ch * row_words)[q];
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // Inverse of the packer for one SNP: byte masks in the reference's layout
 // [genotype][S_pad] (model.c:28-74).  One thread per bit position.
 __global__ void unpack_masks_kernel(const uint32_t *__restrict__ planes, int64_t snp, int64_t snp_pad,
@@ -835,7 +919,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
             const int i0 = meta2.y, j0 = meta2.z, mode = meta2.w;
             const int i = i0 + warp, j = j0 + lane;
             bool valid = (i < j) && (j < a.nv);
-            if (valid) {
+            if (valid && (i <= a.edge_lo || i >= a.edge_hi)) {
                 const uint64_t idx = pair_index((uint64_t) a.nv, (uint64_t) i, (uint64_t) j);
                 valid = idx >= a.first && idx < a.last;
             }
@@ -995,7 +1079,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3_kernel(const Search
             const int i = meta2.y, j0 = meta2.z, k0 = meta2.w;
             const int j = j0 + warp, k = k0 + lane;
             bool valid = (i < j) && (j < k) && (k < a.nv);
-            if (valid) {
+            if (valid && (i <= a.edge_lo || i >= a.edge_hi)) {
                 const uint64_t idx = triple_index((uint64_t) a.nv, (uint64_t) i, (uint64_t) j, (uint64_t) k);
                 valid = idx >= a.first && idx < a.last;
             }
@@ -1059,6 +1143,8 @@ __device__ __forceinline__ bool key_prefix_eq(const Key128 &k, const Key128 &p, 
 }
 
 constexpr int kMergeThreads = 1024;
+constexpr int kMergeSmall = 2048;        // up to this many valid entries per fold are ranked by counting in shared memory
+__host__ __device__ inline size_t merge_smem_bytes(int rank_out) { return (size_t) rank_out * 20 + 16 + (size_t) kMergeSmall * 20; }
 
 __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeArgs m) {
     extern __shared__ __align__(16) uint8_t msmem[];
@@ -1083,17 +1169,47 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeArgs m)
         return c.i >= 0;
     };
 
+    // valid entries are counted and, while they fit, compacted (key, slot) into shared memory
+    Key128 *ckey = reinterpret_cast<Key128 *>(msmem + (((size_t) m.rank_out * 20 + 15) / 16) * 16);   // [kMergeSmall]
+    int *cidx = reinterpret_cast<int *>(ckey + kMergeSmall);                                            // [kMergeSmall]
     if (tid == 0) { prefix.hi = 0; prefix.lo = 0; nsel = 0; nvalid_sh = 0; }
     __syncthreads();
-    {
-        int mine = 0;
-        for (int e = tid; e < total; e += kMergeThreads) {
-            Cand c;
-            mine += entry_valid(e, c) ? 1 : 0;
-        }
-        if (mine) atomicAdd(&nvalid_sh, mine);
+    for (int e = tid; e < total; e += kMergeThreads) {
+        Cand c;
+        if (!entry_valid(e, c)) continue;
+        const int pos = atomicAdd(&nvalid_sh, 1);
+        if (pos < kMergeSmall) { ckey[pos] = cand_key(c, m.order); cidx[pos] = e; }
     }
     __syncthreads();
+    if (nvalid_sh <= kMergeSmall) {
+        // Few entries (the usual case when the score histogram keeps the lists short): keys are unique, so the rank of an
+        // entry is the number of larger keys -- counted against the compacted keys, no selection passes.
+        const int n = nvalid_sh;
+        ModelOut *out = reinterpret_cast<ModelOut *>(m.out) + (size_t) f * m.rank_out;
+        for (int t = tid; t < n; t += kMergeThreads) {
+            const Key128 k = ckey[t];
+            int rank = 0;
+            for (int o = 0; o < n; o++) rank += key_gt(ckey[o], k) ? 1 : 0;
+            if (rank >= m.rank_out) continue;
+            const Cand c = *entry(cidx[t]);
+            ModelOut r;
+            r.accuracy = degenerate ? nan("") : c.ba;
+            r.snp[0] = c.i; r.snp[1] = c.j; r.snp[2] = m.order == 3 ? c.k : -1;
+            r.risky_mask = c.mask;
+            r.conf[0] = (uint32_t) c.tp; r.conf[1] = (uint32_t) (npos - c.tp);
+            r.conf[2] = (uint32_t) c.fp; r.conf[3] = (uint32_t) (nneg - c.fp);
+            out[rank] = r;
+        }
+        for (int t = min(n, m.rank_out) + tid; t < m.rank_out; t += kMergeThreads) {
+            ModelOut r;
+            r.accuracy = nan("");
+            r.snp[0] = r.snp[1] = r.snp[2] = -1;
+            r.risky_mask = 0;
+            r.conf[0] = r.conf[1] = r.conf[2] = r.conf[3] = 0;
+            out[t] = r;
+        }
+        return;
+    }
     const int want = min(m.rank_out, nvalid_sh);
     if (tid == 0) want_sh = want;
     __syncthreads();

@@ -73,6 +73,8 @@ struct SearchArgs {
     int rank;                   // N
     int lists_in_smem;          // per-CTA top-N lists live in shared memory during the search
     uint64_t first, last;       // linear combination index range
+    int edge_lo, edge_hi;       // first SNP of the tuples `first` and `last - 1`: tuples whose first SNP lies strictly between
+                                // are inside the range, only the others are checked index by index
     // work list: order 2 -> unit = (i-tile, j-tile); order 3 -> unit = (i, j-tile); prefix[t] = units before row-group t
     const int64_t *unit_prefix;
     const int32_t *unit_jt0;    // first j-tile of each row group

@@ -129,6 +129,14 @@ class EpistasisEngine:
         self._ck(self.lib.hpgv_epi_last_search_ms(self.h, C.byref(ms), C.byref(grid)))
         return ms.value, grid.value
 
+    def search_times(self, n):
+        """Device durations (ms) of the last n <= 32 search launches, oldest first; one synchronisation."""
+        buf = (C.c_float * max(1, n))()
+        got = self.lib.hpgv_epi_search_times(self.h, n, buf)
+        if got < 0:
+            self._ck(got)
+        return [buf[i] for i in range(got)]
+
     def pipe_peak(self, kind, iters=2000):
         v = C.c_double()
         self._ck(self.lib.hpgv_epi_pipe_peak(self.h, kind, iters, C.byref(v)))

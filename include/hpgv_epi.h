@@ -158,6 +158,11 @@ int hpgv_epi_layout(const hpgv_epi_ctx *ctx, hpgv_epi_layout_t *out);
  * the dominant kernel -- and its grid size.  Blocks until that launch has finished. */
 int hpgv_epi_last_search_ms(hpgv_epi_ctx *ctx, float *ms, int *grid);
 
+/* The same for the last n search launches (n <= 32), oldest first, without a host synchronisation per
+ * launch: a caller that times a loop of steps enqueues them back to back and reads the durations once.
+ * Returns the number of durations written (fewer than n when fewer launches were made). */
+int hpgv_epi_search_times(hpgv_epi_ctx *ctx, int n, float *ms);
+
 /* POPC / LOP3 pipe micro-benchmark (roofline denominator):
  * runs `iters` dependent-free rounds per thread on every SM and returns
  * measured 32-bit ops per second.  kind: 0 = POPC, 1 = LOP3, 2 = POPC+LOP3 mix. */
