@@ -401,7 +401,8 @@ static int apply_folds(hpgv_epi_ctx *ctx, int F, const int32_t *fold_of_sample, 
     const int threads = 256;
     const PackSmem pm = pack_smem_map(ctx->npos, S, fl);
     const char *old_packer = getenv("HPGV_PACK_WARP");          // A/B switch: the one-warp-per-word packer
-    if (pm.total <= 56 * 1024 && !(old_packer && old_packer[0] == '1')) {
+    // (the tri layout's marginals are only written by the staged packer; its permutation always fits)
+    if (pm.total <= 56 * 1024 && (fl.tri || !(old_packer && old_packer[0] == '1'))) {
         // several CTAs per SM hide the latency of the row loads; each walks SNPs blockIdx.x, + gridDim.x, ...
         if (pm.total > 48 * 1024) CK(cudaFuncSetAttribute(pack_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pm.total));
         const int per_sm = (int) std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / pm.total));
@@ -559,20 +560,28 @@ static int build_worklist(hpgv_epi_ctx *ctx, int order, int ti, uint64_t first, 
 struct SearchShape {
     int nthreads = 0;
     bool lists_in_smem = false;
+    int nstages = 2;
     size_t smem = 0;
 };
 static SearchShape pick_shape(const hpgv_epi_ctx *ctx, int order, int rank) {
     const FoldLayout &fl = ctx->fl;
     const int ncells = order == 2 ? 9 : 27;
     SearchShape best;
-    for (int warps = kMaxWarps; warps >= 1; warps >>= 1) {
+    const char *tw_env = getenv("HPGV_TRI_WARPS");               // A/B switch: "16" keeps the tri kernel at 16 warps
+    const bool tri20 = order == 2 && fl.tri && !(tw_env && tw_env[0] == '1' && tw_env[1] == '6');
+    for (int warps = tri20 ? kTriWarps : kMaxWarps; warps >= 1; warps = (warps == kTriWarps ? kMaxWarps : warps >> 1)) {
         const int rows = order == 2 ? warps + kTileJ : 1 + warps + kTileJ;
         for (int in_smem = 1; in_smem >= 0; in_smem--) {
             if (in_smem && (size_t) fl.F * rank * sizeof(Cand) > 24 * 1024) continue;
-            const SmemMap m = search_smem_map(fl, rows, ncells, warps * 32, rank, in_smem != 0);
-            if (m.total <= (size_t) ctx->max_smem_optin) {
-                best.nthreads = warps * 32; best.lists_in_smem = in_smem != 0; best.smem = m.total;
-                return best;
+            // a third stage lets warps drift a step further apart before they wait for each other (order-2 kernel)
+            const char *ns_env = getenv("HPGV_STAGES");
+            const int ns_max = (order == 2 && !(ns_env && ns_env[0] == '2')) ? 3 : 2;
+            for (int ns = ns_max; ns >= 2; ns--) {
+                const SmemMap m = search_smem_map(fl, rows, ncells, warps * 32, rank, in_smem != 0, ns);
+                if (m.total <= (size_t) ctx->max_smem_optin) {
+                    best.nthreads = warps * 32; best.lists_in_smem = in_smem != 0; best.nstages = ns; best.smem = m.total;
+                    return best;
+                }
             }
         }
     }
@@ -600,6 +609,7 @@ static int launch_search(hpgv_epi_ctx *ctx, K kernel, const SearchShape &shape, 
         args.ghist = ctx->d_hist.p;
     }
     args.lists_in_smem = shape.lists_in_smem ? 1 : 0;
+    args.nstages = shape.nstages;
     reset_search_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_gthr.p, ctx->d_hmax.p);
     CK(cudaGetLastError());
     const int slot = (int) (ctx->ev_count % hpgv_epi_ctx::kEvRing);
@@ -659,7 +669,9 @@ static int do_search(hpgv_epi_ctx *ctx, int order, int eval_subset, int rank, ui
     args.last = last;
     {
         const char *st = getenv("HPGV_STAGGER");
-        args.stagger = !(st && st[0] == '0');
+        args.stagger = st && st[0] >= '0' && st[0] <= '2' ? st[0] - '0' : 1;
+        const char *td = getenv("HPGV_TRI_DERIVE");
+        args.tri_derive = !(td && td[0] == '0');
     }
 
     const SearchShape shape = pick_shape(ctx, order, rank);

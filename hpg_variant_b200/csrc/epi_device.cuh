@@ -165,7 +165,7 @@ __host__ __device__ __forceinline__ int64_t plane_word(const FoldLayout &fl, int
 }
 
 // ---- tri layout (FoldLayout::tri) ---------------------------------------------
-// One chunk.  A row is ngroups = nblocks/4 groups of 36 words followed by the tails:
+// One chunk.  A row is ngroups = nblocks/4 groups of 36 words followed by the tails and the per-group marginals:
 //   main word (b, g, w), w < 3 : (b/4)*36 + g*12 + (b%4)*3 + w      (a group = 3 planes x 4 blocks x 3 words = 9 LDS.128)
 //   tail word (m, g), m = b/8  : ngroups*36 + m*4 + g               (one LDS.128 = the three planes of eight blocks' tails)
 // The tail of block b = 4k + q sits in the nibble that the byte counters want: counter word k keeps block q in byte
@@ -175,8 +175,13 @@ __host__ __device__ constexpr uint32_t group_shift(int q) { return q == 0 ? 0u :
 __host__ __device__ __forceinline__ int tri_word_off(int b, int g, int w) { return (b >> 2) * 36 + g * 12 + (b & 3) * 3 + w; }
 __host__ __device__ __forceinline__ int tri_tail_off(int nblocks, int b, int g) { return (nblocks >> 2) * 36 + (b >> 3) * 4 + g; }
 __host__ __device__ __forceinline__ int tri_tail_shift(int b) { return (int) (group_shift(b & 3) / 8 * 2 + ((b >> 2) & 1)) * 4; }
+// After the tails, one LDS.128 per group k: words (N_0, N_1, N_2, missing) -- N_g = the SNP's own per-block counts of
+// genotype g, four byte counters in the layout of the cell counters; missing = 0xFF in the byte of every block in which
+// the SNP has a sample that is in no plane.  In a block without missing samples of SNP i the cells of one genotype of i
+// follow from the others: n(2, gb) = N_gb(j) - n(0, gb) - n(1, gb)  (see tri_group2).
+__host__ __device__ __forceinline__ int tri_marg_off(int nblocks, int k) { return (nblocks >> 2) * 36 + ((nblocks + 7) >> 3) * 4 + k * 4; }
 __host__ __device__ __forceinline__ int tri_row_words(int nblocks) {
-    int rw = (nblocks >> 2) * 36 + ((nblocks + 7) >> 3) * 4;
+    int rw = (nblocks >> 2) * 36 + ((nblocks + 7) >> 3) * 4 + (nblocks >> 2) * 4;
     if ((rw / 4) % 2 == 0) rw += 4;
     return rw;
 }

@@ -127,11 +127,20 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const uint8_t *__restric
             const uint32_t m1 = __ballot_sync(0xffffffffu, g == 1);
             const uint32_t m2 = __ballot_sync(0xffffffffu, g == 2);
             const uint32_t mine = lane == 0 ? m0 : (lane == 1 ? m1 : m2);
+            const uint32_t inno = tri ? __ballot_sync(0xffffffffu, col >= 0 && g > 2u) : 0u;     // samples that are in no plane
             if (lane < 3) {
                 const int o = ofs_s[wb];
                 uint32_t *dst = out_s + r * out_words;
                 if (o >= 0) dst[o + lane * gstride] = mine;
                 else if (mine & 0xFu) atomicOr(dst + ((-o) & 0xFFFFFF) - 1 + lane, (mine & 0xFu) << ((-o) >> 24));
+                if (tri) {
+                    // the SNP's own genotype counts of the block (byte counter of block b in word (b / 4, g)) and its missing flag
+                    const int b = wb >> 2;
+                    uint32_t *mg = dst + tri_marg_off(nblocks, b >> 2);
+                    const uint32_t n = (uint32_t) __popc((wb & 3) == 3 ? (mine & 0xFu) : mine);
+                    if (n) atomicAdd(mg + lane, n << group_shift(b & 3));
+                    if (lane == 0 && inno) atomicOr(mg + 3, 0xFFu << group_shift(b & 3));
+                }
             }
         }
         __syncthreads();
@@ -169,9 +178,9 @@ __global__ void unpack_masks_kernel(const uint32_t *__restrict__ planes, int64_t
 // Shared pieces of the search kernels
 // ============================================================================
 struct __align__(16) SearchCtl {
-    uint64_t full[2];              // per stage: the chunk rows have landed
-    uint64_t empty[2];             // per stage: every warp is done reading it
-    int4 meta[3];                  // step descriptors: x = chunk (-1: no more work), y/z/w = tile origins
+    uint64_t full[3];              // per stage (two or three are in use): the chunk rows have landed
+    uint64_t empty[3];             // per stage: every warp is done reading it
+    int4 meta[4];                  // step descriptors (stages + 1 slots in use): x = chunk (-1: no more work), y/z/w = tile origins
     long long thr[kMaxFolds];      // score a candidate must reach to be offered to the list
     int tq[kMaxFolds];             // the same bound on sum_c max(0, trA - trU) (balanced pre-filter): ceil(thr / n_f)
     int lock[kMaxFolds];
@@ -188,11 +197,12 @@ __host__ __device__ inline int counter_stride(int ncells, int nwc) { return (nce
 struct SmemMap {
     size_t stage0, stage_bytes, counters, desc, lists, total;
 };
-__host__ __device__ inline SmemMap search_smem_map(const FoldLayout &fl, int rows, int ncells, int nthreads, int rank, bool lists_in_smem) {
+__host__ __device__ inline SmemMap search_smem_map(const FoldLayout &fl, int rows, int ncells, int nthreads, int rank, bool lists_in_smem,
+                                                   int nstages = 2) {
     SmemMap m;
     m.stage0 = align_up(sizeof(SearchCtl), 128);
     m.stage_bytes = align_up((size_t) rows * fl.row_words * 4, 128);
-    m.counters = m.stage0 + 2 * m.stage_bytes;
+    m.counters = m.stage0 + (size_t) nstages * m.stage_bytes;
     const int nwc = fl.single ? fl.nblocks / 4 : fl.F;
     m.desc = m.counters + (size_t) counter_stride(ncells, nwc) * nthreads * 4;
     m.lists = align_up(m.desc + (fl.single ? 0 : (size_t) fl.nblocks * 2), 16);
@@ -602,8 +612,12 @@ __device__ __forceinline__ void single_block3(const uint32_t *irow, const uint32
     }
 }
 
-// one group (four blocks) of the tri layout: 36 words of the j row stay in registers, the i row is read plane by plane
-__device__ __forceinline__ void tri_group2(const uint32_t *ig, const uint32_t *jg, uint32_t (&pk)[9]) {
+// one group (four blocks) of the tri layout: 36 words of the j row stay in registers, the i row is read plane by plane.
+// imiss = SNP i's missing mask of the group (0xFF in the byte of a block where i has a sample in no plane, warp-uniform),
+// nj = SNP j's own counts (N_0, N_1, N_2) of the group.  Genotype 2 of SNP i is only counted in the blocks imiss marks;
+// elsewhere every sample of the block has one of the three genotypes of i, so n(2, gb) = N_gb(j) - n(0, gb) - n(1, gb).
+// On entry pk holds the tail counts of the group; the bytes never borrow (N_gb >= n(0, gb) + n(1, gb) in every block).
+__device__ __forceinline__ void tri_group2(const uint32_t *ig, const uint32_t *jg, uint32_t imiss, const uint4 nj, uint32_t (&pk)[9]) {
     uint32_t pj[3][12];
 #pragma unroll
     for (int g = 0; g < 3; g++) {
@@ -614,7 +628,7 @@ __device__ __forceinline__ void tri_group2(const uint32_t *ig, const uint32_t *j
         }
     }
 #pragma unroll
-    for (int ga = 0; ga < 3; ga++) {
+    for (int ga = 0; ga < 2; ga++) {
         uint32_t pi[12];
 #pragma unroll
         for (int q = 0; q < 3; q++) {
@@ -631,18 +645,43 @@ __device__ __forceinline__ void tri_group2(const uint32_t *ig, const uint32_t *j
             pk[ga * 3 + gb] = acc;
         }
     }
+    if (imiss) {                                    // warp-uniform: some block of the group needs genotype 2 counted
+        uint32_t pi[12];
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const uint4 t = *reinterpret_cast<const uint4 *>(ig + 24 + 4 * q);
+            pi[4 * q] = t.x; pi[4 * q + 1] = t.y; pi[4 * q + 2] = t.z; pi[4 * q + 3] = t.w;
+        }
+        auto block = [&](auto qq) {
+            constexpr int q = decltype(qq)::value;
+            if (imiss & (0xFFu << group_shift(q))) {
+#pragma unroll
+                for (int gb = 0; gb < 3; gb++) pk[6 + gb] = tri_count2_acc<(1u << group_shift(q))>(pi + 3 * q, pj[gb] + 3 * q, pk[6 + gb]);
+            }
+        };
+        static_for<4>(block);
+    }
+    const uint32_t njv[3] = {nj.x, nj.y, nj.z};
+#pragma unroll
+    for (int gb = 0; gb < 3; gb++) {
+        const uint32_t derived = njv[gb] - pk[gb] - pk[3 + gb];
+        pk[6 + gb] = (derived & ~imiss) | (pk[6 + gb] & imiss);
+    }
 }
 
 // The counting phase of a tuple is bound by the XU pipe (POPC), its epilogue by the ALU.  Warps of one SM sub-partition
 // that run in lockstep leave each pipe idle half of the time; delaying the upper half of the warps once, by about half
 // the counting time of a unit, lets one half count while the other half evaluates.  (The stage hand-off tolerates a
 // drift of one step, so the offset persists.)
-__device__ __forceinline__ void stagger_late_warps(int warp, int nwarps, int unit_cycles_per_warp) {
-    if (nwarps >= 8 && warp >= nwarps / 2) {
-        const long long wait = (long long) unit_cycles_per_warp * (nwarps / 4) / 2;
-        const long long t0 = clock64();
-        while (clock64() - t0 < wait) {}
-    }
+__device__ __forceinline__ void stagger_late_warps(int warp, int nwarps, int unit_cycles_per_warp, int mode) {
+    // warps w, w + 4, w + 8, ... share a sub-partition; k = the warp's index among them, per = how many there are
+    const int k = warp >> 2, per = (nwarps + 3) >> 2;
+    if (per < 2) return;
+    const long long unit = (long long) unit_cycles_per_warp * per;       // counting time of a unit when the XU is saturated
+    // mode 1: the upper half of each sub-partition's warps starts half a unit late; mode 2: evenly spread phases
+    const long long wait = mode == 2 ? unit * k / per : (k >= (per + 1) / 2 ? unit / 2 : 0);
+    const long long t0 = clock64();
+    while (clock64() - t0 < wait) {}
 }
 
 // once per unit: adopt the best bound any CTA has published for fold f
@@ -706,10 +745,10 @@ template <bool SINGLE>
 __device__ __forceinline__ void search_init(SearchCtl *ctl, const SearchArgs &a, uint32_t *cnt_base, size_t cnt_words, uint16_t *desc) {
     const int tid = threadIdx.x;
     if (tid == 0) {
-        mbar_init(&ctl->full[0], 1);
-        mbar_init(&ctl->full[1], 1);
-        mbar_init(&ctl->empty[0], blockDim.x >> 5);
-        mbar_init(&ctl->empty[1], blockDim.x >> 5);
+        for (int st = 0; st < 3; st++) {
+            mbar_init(&ctl->full[st], 1);
+            mbar_init(&ctl->empty[st], blockDim.x >> 5);
+        }
         mbar_fence_init();
         ctl->fl = *a.fl;
     }
@@ -743,12 +782,13 @@ __device__ __forceinline__ void search_publish(SearchCtl *ctl, const SearchArgs 
 // ============================================================================
 // unit = (i-tile of TI = nwarps rows, j-tile of 32 rows); warp w <-> i = i0 + w; lane <-> j = j0 + lane
 template <int BW, bool SINGLE, bool BALANCED>
-__global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const SearchArgs a) {
+__global__ void __launch_bounds__((BW == 3 ? kTriWarps : kMaxWarps) * 32, 1) search2_kernel(const SearchArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     SearchCtl *ctl = reinterpret_cast<SearchCtl *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nthreads = blockDim.x, TI = nthreads >> 5;
-    const SmemMap sm = search_smem_map(*a.fl, TI + kTileJ, 9, nthreads, a.rank, a.lists_in_smem != 0);
+    const int NS = a.nstages;                       // stages of the ring: 3 when shared memory allows, else 2
+    const SmemMap sm = search_smem_map(*a.fl, TI + kTileJ, 9, nthreads, a.rank, a.lists_in_smem != 0, NS);
     uint32_t *cnt_base = reinterpret_cast<uint32_t *>(smem_raw + sm.counters);
     uint16_t *desc = reinterpret_cast<uint16_t *>(smem_raw + sm.desc);
     Cand *lists = a.lists_in_smem ? reinterpret_cast<Cand *>(smem_raw + sm.lists) : a.lists + (size_t) blockIdx.x * a.fl->F * a.rank;
@@ -771,7 +811,13 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
     // offered) and run again, offers only, after the last unit -- by then the bound keeps nearly all of it out.
     int redo = 0;                                   // 0: main pass, 1: re-running the first unit, 2: no more work
     auto mode_of = [&]() { return !a.use_hist || redo ? kModeOffer : (u == (long long) blockIdx.x ? kModeCount : (kModeCount | kModeOffer)); };
-    auto advance = [&]() {                          // descriptor of the step after the current one
+    bool started = false;
+    auto next_desc = [&]() {                        // descriptors in step order, one per call; x = -1 once the work is done
+        if (!started) {
+            started = true;
+            if (u < a.num_units) { decode(); return make_int4(0, cur_i0, cur_j0, mode_of()); }
+            redo = 2;
+        }
         if (redo == 2) return make_int4(-1, 0, 0, 0);
         if (++chunk == nchunks) {
             chunk = 0;
@@ -792,17 +838,16 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
         bulk_g2s(dst, src + (int64_t) i0 * row_bytes, (uint32_t) TI * row_bytes, &ctl->full[st]);
         bulk_g2s(dst + (size_t) TI * row_bytes, src + (int64_t) j0 * row_bytes, (uint32_t) kTileJ * row_bytes, &ctl->full[st]);
     };
-    // the producer is lane 0 of the LAST warp: it issues the copies of step s + 1 at the top of its own step s
+    // the producer is lane 0 of the LAST warp: at the top of its own step s it issues the copies of step s + NS - 1 into
+    // the stage step s - 1 has used, once every warp has released it; a warp may thus run up to NS - 1 steps ahead of the
+    // slowest one before it has to wait
     const bool producer = (tid == nthreads - 32);
     if (producer) {
-        if (u < a.num_units) {
-            decode();
-            ctl->meta[0] = make_int4(0, cur_i0, cur_j0, mode_of());
-            issue(0, 0, cur_i0, cur_j0);
-        } else {
-            redo = 2;
-            ctl->meta[0] = make_int4(-1, 0, 0, 0);
-            mbar_arrive(&ctl->full[0]);
+        for (int t = 0; t < NS - 1; t++) {
+            const int4 d = next_desc();
+            ctl->meta[t] = d;
+            if (d.x >= 0) issue(t, d.x, d.y, d.z);
+            else mbar_arrive(&ctl->full[t]);                                   // end marker: a phase without data
         }
     }
 
@@ -812,21 +857,25 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
 #pragma unroll
     for (int c = 0; c < 9; c++) acc[c] = 0;
 
+    int st = 0, slot = 0;                           // s % NS, s % (NS + 1)
+    uint32_t ph = 0;                                // (s / NS) & 1
     for (uint32_t s = 0;; s++) {
-        const int st = s & 1;
         if (producer) {
-            const int4 next = advance();
-            ctl->meta[(s + 1) % 3] = next;
-            if (s >= 1) mbar_wait(&ctl->empty[st ^ 1], ((s - 1) >> 1) & 1);   // every warp has read step s - 1
-            if (next.x >= 0) issue(st ^ 1, next.x, next.y, next.z);
-            else mbar_arrive(&ctl->full[st ^ 1]);                              // end marker: a phase without data
+            const int4 next = next_desc();          // step s + NS - 1
+            int tslot = slot + NS - 1;
+            if (tslot > NS) tslot -= NS + 1;
+            ctl->meta[tslot] = next;
+            const int tst = st == 0 ? NS - 1 : st - 1;                         // its stage: the one of step s - 1
+            if (s >= 1) mbar_wait(&ctl->empty[tst], st == 0 ? ph ^ 1u : ph);   // every warp has read step s - 1
+            if (next.x >= 0) issue(tst, next.x, next.y, next.z);
+            else mbar_arrive(&ctl->full[tst]);
         }
         __syncwarp();
-        mbar_wait(&ctl->full[st], (s >> 1) & 1);
-        const int4 meta = ctl->meta[s % 3];
+        mbar_wait(&ctl->full[st], ph);
+        const int4 meta = ctl->meta[slot];
         if (meta.x < 0) break;
         const int ch = meta.x;
-        if (s == 0 && a.stagger) stagger_late_warps(warp, TI, nblocks * 9 * (BW == 3 ? 18 : (BW == 4 ? 24 : 34)));
+        if (s == 0 && a.stagger) stagger_late_warps(warp, TI, nblocks * 9 * (BW == 3 ? 18 : (BW == 4 ? 24 : 34)), a.stagger);
         if (ch == 0) {
             if (a.use_hist) {
                 // every unit at first, then ever more rarely: the bound rises with the logarithm of the pairs seen, and
@@ -846,7 +895,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
 
         if constexpr (BW == 3) {
             // tri layout (one chunk): two groups of four blocks share a tail word
-            const int ngroups = nblocks >> 2;
+            const int ngroups = nblocks >> 2, ntail = (nblocks + 7) >> 3;
             const uint32_t *itail = irow + ngroups * 36, *jtail = jrow + ngroups * 36;
             for (int m = 0; 2 * m < ngroups; m++) {
                 uint32_t pk0[9], pk1[9];
@@ -861,11 +910,15 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
 #pragma unroll
                         for (int gb = 0; gb < 3; gb++) tail_count_acc(tiv[ga] & tjv[gb], pk0[ga * 3 + gb], pk1[ga * 3 + gb]);
                 }
-                tri_group2(irow + (2 * m) * 36, jrow + (2 * m) * 36, pk0);
+                const uint32_t *imarg = irow + ngroups * 36 + ntail * 4, *jmarg = jrow + ngroups * 36 + ntail * 4;
+                const uint32_t derive_off = a.tri_derive ? 0u : 0xFFFFFFFFu;     // A/B switch: count every block directly
+                tri_group2(irow + (2 * m) * 36, jrow + (2 * m) * 36, imarg[4 * (2 * m) + 3] | derive_off,
+                           *reinterpret_cast<const uint4 *>(jmarg + 4 * (2 * m)), pk0);
 #pragma unroll
                 for (int c = 0; c < 9; c++) cnts[(2 * m) * 9 + c] = pk0[c];
                 if (2 * m + 1 < ngroups) {
-                    tri_group2(irow + (2 * m + 1) * 36, jrow + (2 * m + 1) * 36, pk1);
+                    tri_group2(irow + (2 * m + 1) * 36, jrow + (2 * m + 1) * 36, imarg[4 * (2 * m + 1) + 3] | derive_off,
+                               *reinterpret_cast<const uint4 *>(jmarg + 4 * (2 * m + 1)), pk1);
 #pragma unroll
                     for (int c = 0; c < 9; c++) cnts[(2 * m + 1) * 9 + c] = pk1[c];
                 }
@@ -912,7 +965,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
         __syncwarp();
         // the step descriptor is read again here (its slot is rewritten two steps later, which needs this warp's
         // arrival below) so that the tile origins hold no registers during the counting phase
-        const int4 meta2 = ld_volatile_shared_int4(&ctl->meta[s % 3]);
+        const int4 meta2 = ld_volatile_shared_int4(&ctl->meta[slot]);
         if (lane == 0) mbar_arrive(&ctl->empty[st]);        // this warp is done with the stage
 
         if (meta2.x == nchunks - 1) {
@@ -928,6 +981,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search2_kernel(const Search
                 else epilogue_general<9, SINGLE>(ctl, a, lists, cnts, nwc, nthreads, valid, i, j, -1, lane);
             }
         }
+        if (++st == NS) { st = 0; ph ^= 1u; }
+        if (++slot > NS) slot = 0;
     }
     search_publish(ctl, a, lists);
 }
@@ -1015,7 +1070,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3_kernel(const Search
         const int4 meta = ctl->meta[s % 3];
         if (meta.x < 0) break;
         const int ch = meta.x;
-        if (s == 0 && a.stagger) stagger_late_warps(warp, TJ, nblocks * 27 * (BW == 4 ? 24 : 34));
+        if (s == 0 && a.stagger) stagger_late_warps(warp, TJ, nblocks * 27 * (BW == 4 ? 24 : 34), a.stagger);
         if (ch == 0 && warp == 0 && lane < ctl->fl.F) refresh_threshold(ctl, a, lane);
 
         const uint32_t *sbase = reinterpret_cast<const uint32_t *>(smem_raw + sm.stage0 + (size_t) st * sm.stage_bytes);

@@ -10,6 +10,7 @@ constexpr int kMaxBlocks = 4096;          // sample-axis blocks per SNP row (256
 constexpr int kMaxRank   = 4096;          // HPGV_MAX_RANK
 constexpr int kTileJ     = 32;            // one j (or k) SNP per lane
 constexpr int kMaxWarps  = 16;            // consumer warps per CTA = i (or j) rows per tile
+constexpr int kTriWarps  = 20;            // the tri order-2 kernel fits 96 registers: five warps per SM sub-partition
 
 // Per-fold sizes and the segmented sample layout chosen by set_folds().
 //
@@ -90,7 +91,9 @@ struct SearchArgs {
     int *ghmax;                 // [F] largest score counted so far (-1: none)
     int hist_bins;              // A + 1
     int use_hist;
-    int stagger;                // delay the upper half of the warps once by half a unit (HPGV_STAGGER=0 turns it off)
+    int tri_derive;             // tri layout: derive genotype 2 of SNP i from SNP j's marginals in blocks where i has no missing sample
+    int nstages;                // shared-memory stages of the search kernel's ring (2 or 3)
+    int stagger;                // 1: half of each sub-partition's warps starts half a unit late, 2: evenly spread phases, 0: off (HPGV_STAGGER)
 };
 
 }  // namespace hpgv
