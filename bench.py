@@ -45,7 +45,7 @@ FOLD_SEED = 20261017
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
@@ -344,9 +344,12 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    # DRAM bytes of one search launch from the committed `ncu --set full` capture of the same command (profiles/)
+    ncu_traffic = {"c2": {"bytes": 8591872 + 2304, "source": "profiles/r01d_search2_c2_ncu_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum)"}}
+    tr = ncu_traffic.get(args.workload) if (world == 1 and not args.snps) else None
     roofline = {
         "bound": "int_popc", "kernel": f"search{order}_kernel", "achieved": achieved / 1e12, "peak": popc_peak / 1e12, "unit": "TPOPC32/s",
-        "frac": achieved / popc_peak, "traffic": None,
+        "frac": achieved / popc_peak, "traffic": tr["bytes"] if tr else None, "traffic_source": tr["source"] if tr else None,
         "algorithmic": f"3^{order} x W = {popc_per_comb} POPC32 per combination (W = {Wwords} words), {my_combs} combinations per launch",
         "peak_source": "POPC micro-benchmark in this run (hpgv_epi_pipe_peak), all SMs",
         "kernel_ms": k_ms, "kernel_share_of_step": k_ms * args.steps / (sum(a.elapsed_time(b) for a, b in ev)),
