@@ -332,10 +332,13 @@ static int apply_folds(hpgv_epi_ctx *ctx, int F, const int32_t *fold_of_sample, 
     const bool tri_fits = fl.single && max_seg <= 100 && nb <= 24;
     fl.tri = (allow_tri && tri_fits) ? 1 : 0;
     ctx->tri_suppressed = tri_fits && !allow_tri;
+    ctx->npos = (int64_t) nb * bits_per_block;
+    fl.marg = 0; fl.marg_off = 0;
     if (fl.tri) {
         fl.bw = 4;                                       // logical positions: word 3 of a block = its 4-bit tail
         fl.cb = nb; fl.nchunks = 1;
         fl.row_words = tri_row_words(nb);
+        fl.marg = 1; fl.marg_off = tri_marg_off(nb, 0);
     } else {
     // chunks: a stage of the search kernels holds (16 + 32 + 1) chunk rows; keep it within 48 KB
         const int block_bytes = 3 * fl.bw * 4;
@@ -345,15 +348,23 @@ static int apply_folds(hpgv_epi_ctx *ctx, int F, const int32_t *fold_of_sample, 
         fl.cb = (nb + fl.nchunks - 1) / fl.nchunks;
         if (fl.single) fl.cb = (fl.cb + 3) / 4 * 4;
         fl.nchunks = (nb + fl.cb - 1) / fl.cb;
-        fl.row_words = fl.cb * 3 * fl.bw;
-        if ((fl.row_words / 4) % 2 == 0) fl.row_words += 4;   // odd number of 16-byte groups per row: conflict-free LDS.128
+        // single-block segments: the per-group marginals follow the planes of a chunk row when the staged packer (which
+        // writes them) can run and a stage of 49 rows still fits 48 KB
+        const char *old_packer = getenv("HPGV_PACK_WARP");
+        for (int with_marg = (fl.single && !(old_packer && old_packer[0] == '1')) ? 1 : 0; with_marg >= 0; with_marg--) {
+            fl.marg = with_marg;
+            fl.marg_off = fl.cb * 3 * fl.bw;
+            fl.row_words = fl.cb * 3 * fl.bw + (with_marg ? fl.cb : 0);
+            if ((fl.row_words / 4) % 2 == 0) fl.row_words += 4;   // odd number of 16-byte groups per row: conflict-free LDS.128
+            if (!with_marg) break;
+            if (pack_smem_map(ctx->npos, S, fl).total <= 56 * 1024 && (size_t) (kMaxWarps + kTileJ + 1) * fl.row_words * 4 <= 48 * 1024) break;
+        }
     }
     ctx->blk.assign(nb, (uint16_t) 0x7fff);            // padding blocks belong to no segment
     for (int s = 0; s < 2 * F; s++)
         for (int b = 0; b < seg_blocks[s]; b++)
             ctx->blk[seg_first[s] + b] = (uint16_t) (s | (b == seg_blocks[s] - 1 ? 0x8000 : 0));
     (void) nb_real;
-    ctx->npos = (int64_t) nb * bits_per_block;
     ctx->perm.assign((size_t) ctx->npos, -1);
     {
         std::vector<int> fill(2 * F, 0);
@@ -568,7 +579,7 @@ static SearchShape pick_shape(const hpgv_epi_ctx *ctx, int order, int rank) {
     const int ncells = order == 2 ? 9 : 27;
     SearchShape best;
     const char *tw_env = getenv("HPGV_TRI_WARPS");               // A/B switch: "16" keeps the tri kernel at 16 warps
-    const bool tri20 = order == 2 && fl.tri && !(tw_env && tw_env[0] == '1' && tw_env[1] == '6');
+    const bool tri20 = order == 2 && fl.single && !(tw_env && tw_env[0] == '1' && tw_env[1] == '6');
     for (int warps = tri20 ? kTriWarps : kMaxWarps; warps >= 1; warps = (warps == kTriWarps ? kMaxWarps : warps >> 1)) {
         const int rows = order == 2 ? warps + kTileJ : 1 + warps + kTileJ;
         for (int in_smem = 1; in_smem >= 0; in_smem--) {

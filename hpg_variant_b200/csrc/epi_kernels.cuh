@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const uint8_t *__restric
     uint32_t *out_s = reinterpret_cast<uint32_t *>(psm + m.out);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int bw = flp->bw, lbw = bw == 8 ? 3 : 2, nwords = flp->nblocks * bw, tri = flp->tri, cb = flp->cb, nblocks = flp->nblocks;
-    const int row_words = flp->row_words, nchunks = flp->nchunks;
+    const int row_words = flp->row_words, nchunks = flp->nchunks, marg = flp->marg, marg_off = flp->marg_off;
     const int out_words = nchunks * row_words;                           // per SNP, chunk-major
     const int gstride = tri ? 12 : bw;                                   // words between the planes of one block
     for (int64_t x = tid; x < npos; x += blockDim.x) perm_s[x] = perm[x];
@@ -127,17 +127,17 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const uint8_t *__restric
             const uint32_t m1 = __ballot_sync(0xffffffffu, g == 1);
             const uint32_t m2 = __ballot_sync(0xffffffffu, g == 2);
             const uint32_t mine = lane == 0 ? m0 : (lane == 1 ? m1 : m2);
-            const uint32_t inno = tri ? __ballot_sync(0xffffffffu, col >= 0 && g > 2u) : 0u;     // samples that are in no plane
+            const uint32_t inno = marg ? __ballot_sync(0xffffffffu, col >= 0 && g > 2u) : 0u;    // samples that are in no plane
             if (lane < 3) {
                 const int o = ofs_s[wb];
                 uint32_t *dst = out_s + r * out_words;
                 if (o >= 0) dst[o + lane * gstride] = mine;
                 else if (mine & 0xFu) atomicOr(dst + ((-o) & 0xFFFFFF) - 1 + lane, (mine & 0xFu) << ((-o) >> 24));
-                if (tri) {
+                if (marg) {
                     // the SNP's own genotype counts of the block (byte counter of block b in word (b / 4, g)) and its missing flag
-                    const int b = wb >> 2;
-                    uint32_t *mg = dst + tri_marg_off(nblocks, b >> 2);
-                    const uint32_t n = (uint32_t) __popc((wb & 3) == 3 ? (mine & 0xFu) : mine);
+                    const int b = wb >> lbw;
+                    uint32_t *mg = dst + (tri ? marg_off + (b >> 2) * 4 : (b / cb) * row_words + marg_off + ((b % cb) >> 2) * 4);
+                    const uint32_t n = (uint32_t) __popc(tri && (wb & 3) == 3 ? (mine & 0xFu) : mine);
                     if (n) atomicAdd(mg + lane, n << group_shift(b & 3));
                     if (lane == 0 && inno) atomicOr(mg + 3, 0xFFu << group_shift(b & 3));
                 }
@@ -575,18 +575,31 @@ __device__ __forceinline__ void epilogue_balanced(SearchCtl *ctl, const SearchAr
 // (2k A, 2k U, 2k+1 A, 2k+1 U) land in bytes (0, 2, 1, 3), i.e. the word reads (A_2k, A_2k+1, U_2k, U_2k+1)
 
 // block Q (0..3) of a four-block group, single-block segments: the nine (27) cell counts go to byte group_shift(Q) of pk[]
+// imiss: SNP i's missing mask of the four-block group (warp-uniform); genotype 2 of SNP i is only counted in the blocks it
+// marks, the others get it from SNP j's marginals afterwards (derive_row2)
 template <int BW, int Q>
-__device__ __forceinline__ void single_block2(const uint32_t *irow, const uint32_t *jrow, uint32_t (&pk)[9]) {
+__device__ __forceinline__ void single_block2(const uint32_t *irow, const uint32_t *jrow, uint32_t imiss, uint32_t (&pk)[9]) {
     constexpr int SW = slot_words(BW), off = Q * 3 * SW;
     uint32_t pj[3][BW];
 #pragma unroll
     for (int g = 0; g < 3; g++) load_plane<BW>(jrow + off + g * SW, pj[g]);
 #pragma unroll
     for (int ga = 0; ga < 3; ga++) {
+        if (ga == 2 && !(imiss & (0xFFu << group_shift(Q)))) break;
         uint32_t pi[BW];
         load_plane<BW>(irow + off + ga * SW, pi);
 #pragma unroll
         for (int gb = 0; gb < 3; gb++) pk[ga * 3 + gb] = cell_count2_acc<BW, (1u << group_shift(Q))>(pi, pj[gb], pk[ga * 3 + gb]);
+    }
+}
+// In a block where SNP i has no missing sample every sample has one of i's three genotypes:
+// n(2, gb) = N_gb(j) - n(0, gb) - n(1, gb), byte by byte (the bytes never borrow: N_gb >= n(0, gb) + n(1, gb) in every block)
+__device__ __forceinline__ void derive_row2(uint32_t imiss, const uint4 nj, uint32_t (&pk)[9]) {
+    const uint32_t njv[3] = {nj.x, nj.y, nj.z};
+#pragma unroll
+    for (int gb = 0; gb < 3; gb++) {
+        const uint32_t derived = njv[gb] - pk[gb] - pk[3 + gb];
+        pk[6 + gb] = (derived & ~imiss) | (pk[6 + gb] & imiss);
     }
 }
 template <int BW, int Q>
@@ -661,12 +674,7 @@ __device__ __forceinline__ void tri_group2(const uint32_t *ig, const uint32_t *j
         };
         static_for<4>(block);
     }
-    const uint32_t njv[3] = {nj.x, nj.y, nj.z};
-#pragma unroll
-    for (int gb = 0; gb < 3; gb++) {
-        const uint32_t derived = njv[gb] - pk[gb] - pk[3 + gb];
-        pk[6 + gb] = (derived & ~imiss) | (pk[6 + gb] & imiss);
-    }
+    derive_row2(imiss, nj, pk);
 }
 
 // The counting phase of a tuple is bound by the XU pipe (POPC), its epilogue by the ALU.  Warps of one SM sub-partition
@@ -782,7 +790,7 @@ __device__ __forceinline__ void search_publish(SearchCtl *ctl, const SearchArgs 
 // ============================================================================
 // unit = (i-tile of TI = nwarps rows, j-tile of 32 rows); warp w <-> i = i0 + w; lane <-> j = j0 + lane
 template <int BW, bool SINGLE, bool BALANCED>
-__global__ void __launch_bounds__((BW == 3 ? kTriWarps : kMaxWarps) * 32, 1) search2_kernel(const SearchArgs a) {
+__global__ void __launch_bounds__((SINGLE ? kTriWarps : kMaxWarps) * 32, 1) search2_kernel(const SearchArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     SearchCtl *ctl = reinterpret_cast<SearchCtl *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -929,10 +937,18 @@ __global__ void __launch_bounds__((BW == 3 ? kTriWarps : kMaxWarps) * 32, 1) sea
 #pragma unroll
                 for (int c = 0; c < 9; c++) pk[c] = 0;
                 const int off = (b4 - b_lo) * 3 * SW;
-                single_block2<BW, 0>(irow + off, jrow + off, pk);
-                single_block2<BW, 1>(irow + off, jrow + off, pk);
-                single_block2<BW, 2>(irow + off, jrow + off, pk);
-                single_block2<BW, 3>(irow + off, jrow + off, pk);
+                uint32_t imiss = 0xFFFFFFFFu;                                   // without marginals every block is counted
+                uint4 nj = make_uint4(0u, 0u, 0u, 0u);
+                if (ctl->fl.marg && a.tri_derive) {
+                    const int mq = ctl->fl.marg_off + (b4 - b_lo);              // one quad per four blocks
+                    imiss = irow[mq + 3];
+                    nj = *reinterpret_cast<const uint4 *>(jrow + mq);
+                }
+                single_block2<BW, 0>(irow + off, jrow + off, imiss, pk);
+                single_block2<BW, 1>(irow + off, jrow + off, imiss, pk);
+                single_block2<BW, 2>(irow + off, jrow + off, imiss, pk);
+                single_block2<BW, 3>(irow + off, jrow + off, imiss, pk);
+                derive_row2(imiss, nj, pk);
                 const int k = b4 >> 2;
 #pragma unroll
                 for (int c = 0; c < 9; c++) cnts[k * 9 + c] = pk[c];

@@ -10,7 +10,7 @@ constexpr int kMaxBlocks = 4096;          // sample-axis blocks per SNP row (256
 constexpr int kMaxRank   = 4096;          // HPGV_MAX_RANK
 constexpr int kTileJ     = 32;            // one j (or k) SNP per lane
 constexpr int kMaxWarps  = 16;            // consumer warps per CTA = i (or j) rows per tile
-constexpr int kTriWarps  = 20;            // the tri order-2 kernel fits 96 registers: five warps per SM sub-partition
+constexpr int kTriWarps  = 20;            // the order-2 kernels with byte counters fit 96 registers: five warps per SM sub-partition
 
 // Per-fold sizes and the segmented sample layout chosen by set_folds().
 //
@@ -41,6 +41,10 @@ struct FoldLayout {
                            // 4-bit tail per segment, the tails of eight segments sharing one word (see tri_* in epi_device.cuh):
                            // 3 words compress to 2 POPC, the tails are counted with nibble-wise adds on the ALU.  Logical
                            // bit positions stay those of bw = 4 (word 3 of a block = its tail, bits 0..3).
+    int marg;              // rows carry, per group of four blocks, one 16-byte quad (N_0, N_1, N_2, missing): the SNP's own
+                           // per-block genotype counts as packed byte counters and 0xFF in the byte of every block where the
+                           // SNP has a sample in no plane (tri layout: always; single-block layouts: when the staged packer runs)
+    int marg_off;          // word offset of the first quad inside a chunk row
     int nblocks;           // real blocks along the sample axis (single: nseg rounded up to a multiple of 4)
     int cb;                // blocks per chunk (single: multiple of 4)
     int nchunks;
@@ -91,7 +95,7 @@ struct SearchArgs {
     int *ghmax;                 // [F] largest score counted so far (-1: none)
     int hist_bins;              // A + 1
     int use_hist;
-    int tri_derive;             // tri layout: derive genotype 2 of SNP i from SNP j's marginals in blocks where i has no missing sample
+    int tri_derive;             // derive genotype 2 of SNP i from SNP j's marginals in blocks where i has no missing sample (rows with marg)
     int nstages;                // shared-memory stages of the search kernel's ring (2 or 3)
     int stagger;                // 1: half of each sub-partition's warps starts half a unit late, 2: evenly spread phases, 0: off (HPGV_STAGGER)
 };
