@@ -357,7 +357,7 @@ static int apply_folds(hpgv_epi_ctx *ctx, int F, const int32_t *fold_of_sample, 
             fl.row_words = fl.cb * 3 * fl.bw + (with_marg ? fl.cb : 0);
             if ((fl.row_words / 4) % 2 == 0) fl.row_words += 4;   // odd number of 16-byte groups per row: conflict-free LDS.128
             if (!with_marg) break;
-            if (pack_smem_map(ctx->npos, S, fl).total <= 56 * 1024 && (size_t) (kMaxWarps + kTileJ + 1) * fl.row_words * 4 <= 48 * 1024) break;
+            if (pack_smem_map(ctx->npos, S, fl).total <= 96 * 1024 && (size_t) (kMaxWarps + kTileJ + 1) * fl.row_words * 4 <= 48 * 1024) break;
         }
     }
     ctx->blk.assign(nb, (uint16_t) 0x7fff);            // padding blocks belong to no segment
@@ -413,11 +413,13 @@ static int apply_folds(hpgv_epi_ctx *ctx, int F, const int32_t *fold_of_sample, 
     const PackSmem pm = pack_smem_map(ctx->npos, S, fl);
     const char *old_packer = getenv("HPGV_PACK_WARP");          // A/B switch: the one-warp-per-word packer
     // (the tri layout's marginals are only written by the staged packer; its permutation always fits)
-    if (pm.total <= 56 * 1024 && (fl.tri || !(old_packer && old_packer[0] == '1'))) {
+    if (pm.total <= 96 * 1024 && (fl.tri || !(old_packer && old_packer[0] == '1'))) {
         // several CTAs per SM hide the latency of the row loads; each walks SNPs blockIdx.x, + gridDim.x, ...
         if (pm.total > 48 * 1024) CK(cudaFuncSetAttribute(pack_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pm.total));
         const int per_sm = (int) std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / pm.total));
-        const int64_t grid = std::min<int64_t>((ctx->nv + kPackRows - 1) / kPackRows, (int64_t) ctx->num_sms * per_sm);
+        const int64_t batches = (ctx->nv + kPackRows - 1) / kPackRows;
+        int64_t grid = std::min<int64_t>(batches, (int64_t) ctx->num_sms * per_sm);
+        grid = (batches + (batches + grid - 1) / grid - 1) / ((batches + grid - 1) / grid);     // every CTA the same number of batches
         pack_rows_kernel<<<(unsigned) grid, threads, pm.total, ctx->stream>>>(ctx->d_raw, ctx->nv, S, ctx->d_perm.p, ctx->d_fl.p, ctx->snp_pad,
                                                                               ctx->npos, ctx->d_planes.p);
     } else {

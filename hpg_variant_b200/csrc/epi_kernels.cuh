@@ -70,12 +70,12 @@ __global__ void pack_planes_kernel(const uint8_t *__restrict__ raw, int64_t nv, 
 struct PackSmem {
     size_t perm, ofs, row, out, total;
 };
-constexpr int kPackRows = 4;      // SNPs a CTA packs per iteration (their rows are contiguous on both sides)
+constexpr int kPackRows = 8;      // SNPs a CTA packs per iteration (their rows are contiguous on both sides)
 __host__ __device__ inline PackSmem pack_smem_map(int64_t npos, int64_t nsamples, const FoldLayout &fl) {
     PackSmem m;
     m.perm = 0;
-    m.ofs = (size_t) npos * 4;                                           // one int per logical word (npos / 32 of them)
-    m.row = m.ofs + (((size_t) (npos / 32) * 4 + 15) / 16) * 16;
+    m.ofs = (size_t) npos * 4;                                           // two ints per logical word (npos / 32 of them)
+    m.row = m.ofs + (((size_t) (npos / 32) * 8 + 15) / 16) * 16;
     m.out = m.row + (((size_t) nsamples * kPackRows + 15) / 16 + 1) * 16;   // + 16: staged at the global misalignment
     m.total = m.out + (size_t) kPackRows * fl.nchunks * fl.row_words * 4;
     return m;
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const uint8_t *__restric
     extern __shared__ __align__(16) uint8_t psm[];
     const PackSmem m = pack_smem_map(npos, nsamples, *flp);
     int32_t *perm_s = reinterpret_cast<int32_t *>(psm + m.perm);
-    int32_t *ofs_s = reinterpret_cast<int32_t *>(psm + m.ofs);
+    int2 *ofs_s = reinterpret_cast<int2 *>(psm + m.ofs);
     uint8_t *row_s = psm + m.row;
     uint32_t *out_s = reinterpret_cast<uint32_t *>(psm + m.out);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -94,14 +94,18 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const uint8_t *__restric
     const int row_words = flp->row_words, nchunks = flp->nchunks, marg = flp->marg, marg_off = flp->marg_off;
     const int out_words = nchunks * row_words;                           // per SNP, chunk-major
     const int gstride = tri ? 12 : bw;                                   // words between the planes of one block
+    const int bpt = flp->single ? 4 : 1;                                 // blocks per task (nblocks is a multiple of 4 then)
+    const int tasks_per_row = nblocks / bpt;
     for (int64_t x = tid; x < npos; x += blockDim.x) perm_s[x] = perm[x];
-    // where logical word wb of plane 0 goes inside the staged output of one SNP; tri tails: -(offset + 1) | shift << 24
+    // x: where logical word wb of plane 0 goes inside the staged output of one SNP; tri tails: -(offset + 1) | shift << 24
+    // y: the marginal quad of its block | byte shift of the block's counter << 24 | 1 << 30 when the word is a tri tail
     for (int wb = tid; wb < nwords; wb += blockDim.x) {
         const int b = wb >> lbw, w = wb & (bw - 1);
         int o;
         if (tri) o = w < 3 ? tri_word_off(b, 0, w) : -((tri_tail_off(nblocks, b, 0) + 1) | (tri_tail_shift(b) << 24));
         else o = (b / cb) * row_words + ((b % cb) * 3) * bw + w;
-        ofs_s[wb] = o;
+        const int mq = tri ? marg_off + (b >> 2) * 4 : (b / cb) * row_words + marg_off + ((b % cb) >> 2) * 4;
+        ofs_s[wb] = make_int2(o, mq | ((int) group_shift(b & 3) << 24) | ((tri && w == 3) ? (1 << 30) : 0));
     }
     for (int64_t snp0 = (int64_t) blockIdx.x * kPackRows; snp0 < nv; snp0 += (int64_t) gridDim.x * kPackRows) {
         const int nr = (int) min((int64_t) kPackRows, nv - snp0);
@@ -119,28 +123,45 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const uint8_t *__restric
         }
         for (int x = tid; x < nr * out_words; x += blockDim.x) out_s[x] = 0;
         __syncthreads();
-        for (int r = 0; r < nr; r++)
-        for (int wb = warp; wb < nwords; wb += nwarps) {
-            const int32_t col = perm_s[wb * 32 + lane];
-            const uint32_t g = col >= 0 ? row_s[mis + r * nsamples + col] : 255u;
-            const uint32_t m0 = __ballot_sync(0xffffffffu, g == 0);
-            const uint32_t m1 = __ballot_sync(0xffffffffu, g == 1);
-            const uint32_t m2 = __ballot_sync(0xffffffffu, g == 2);
-            const uint32_t mine = lane == 0 ? m0 : (lane == 1 ? m1 : m2);
-            const uint32_t inno = marg ? __ballot_sync(0xffffffffu, col >= 0 && g > 2u) : 0u;    // samples that are in no plane
-            if (lane < 3) {
-                const int o = ofs_s[wb];
-                uint32_t *dst = out_s + r * out_words;
-                if (o >= 0) dst[o + lane * gstride] = mine;
-                else if (mine & 0xFu) atomicOr(dst + ((-o) & 0xFFFFFF) - 1 + lane, (mine & 0xFu) << ((-o) >> 24));
-                if (marg) {
-                    // the SNP's own genotype counts of the block (byte counter of block b in word (b / 4, g)) and its missing flag
-                    const int b = wb >> lbw;
-                    uint32_t *mg = dst + (tri ? marg_off + (b >> 2) * 4 : (b / cb) * row_words + marg_off + ((b % cb) >> 2) * 4);
-                    const uint32_t n = (uint32_t) __popc(tri && (wb & 3) == 3 ? (mine & 0xFu) : mine);
-                    if (n) atomicAdd(mg + lane, n << group_shift(b & 3));
-                    if (lane == 0 && inno) atomicOr(mg + 3, 0xFFu << group_shift(b & 3));
+        // one warp per (SNP, counter group of four blocks) when the rows carry marginals, else per (SNP, block): the
+        // group's own genotype counts, its missing mask and the tri tails are assembled in registers (lane g = plane g)
+        for (int task = warp; task < nr * tasks_per_row; task += nwarps) {
+            const int r = task / tasks_per_row, tg = task - r * tasks_per_row;
+            uint32_t *dst = out_s + r * out_words;
+            const uint8_t *row = row_s + mis + (size_t) r * nsamples;
+            uint32_t nacc = 0, missacc = 0, tailacc = 0;
+            int tail_o = 0, mq = 0;
+            for (int q = 0; q < bpt; q++) {
+                const int b = tg * bpt + q;
+                uint32_t n = 0, inno_any = 0;
+                for (int w = 0; w < bw; w++) {
+                    const int wb = b * bw + w;
+                    const int32_t col = perm_s[wb * 32 + lane];
+                    const uint32_t g = col >= 0 ? row[col] : 255u;
+                    const uint32_t m0 = __ballot_sync(0xffffffffu, g == 0);
+                    const uint32_t m1 = __ballot_sync(0xffffffffu, g == 1);
+                    const uint32_t m2 = __ballot_sync(0xffffffffu, g == 2);
+                    if (marg) inno_any |= __ballot_sync(0xffffffffu, col >= 0 && g > 2u);      // samples that are in no plane
+                    uint32_t mine = lane == 0 ? m0 : (lane == 1 ? m1 : m2);
+                    const int2 om = ofs_s[wb];
+                    mq = om.y & 0xFFFFFF;
+                    if (om.x >= 0) {
+                        if (lane < 3) dst[om.x + lane * gstride] = mine;
+                    } else {                                                                     // tri tail: four bits of this block
+                        mine &= 0xFu;
+                        tailacc |= mine << ((-om.x) >> 24);
+                        tail_o = ((-om.x) & 0xFFFFFF) - 1;
+                    }
+                    n += (uint32_t) __popc(mine);
                 }
+                nacc += n << group_shift(q);                        // bpt == 4 whenever marg is set: q = b & 3
+                if (inno_any) missacc |= 0xFFu << group_shift(q);
+            }
+            if (lane < 3) {
+                if (tailacc) atomicOr(dst + tail_o + lane, tailacc);     // the tail word is shared with the neighbouring group
+                if (marg) dst[mq + lane] = nacc;
+            } else if (lane == 3 && marg) {
+                dst[mq + 3] = missacc;
             }
         }
         __syncthreads();
