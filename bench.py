@@ -98,9 +98,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples taken inside [t0, t1] (perf_counter); nvidia-smi needs about a second to start, so it is launched
+        before the warm-up and the window is cut out afterwards."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         self.proc.terminate()
@@ -108,8 +110,14 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        rows = [r for (t, r) in self.rows if t0 is None or (t0 <= t <= t1 + 0.15)]
+        window = "timed region"
+        if not rows and self.rows:           # region shorter than the sampling period: the samples next to it
+            mid = 0.5 * (t0 + t1)
+            rows = [r for (t, r) in sorted(self.rows, key=lambda x: abs(x[0] - mid))[:3]]
+            window = "nearest samples (the timed region is shorter than the sampling period)"
         sm, smax, reasons = [], None, set()
-        for r in self.rows:
+        for r in rows:
             p = [x.strip() for x in r.split(",")]
             if len(p) < 6:
                 continue
@@ -121,7 +129,8 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm),
+                "window": window}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -268,11 +277,24 @@ def main():
     d_local, d_all, d_final = shard.d_local, shard.d_all, shard.d_final
     h_out = np.zeros((F, RANK_SIZE), h.MODEL_DTYPE)
 
-    def step_device():
+    phase_ev = []
+
+    def step_device(record=False):
         """pack + search (+ all-gather + merge) with the genotype bytes resident in HBM"""
         eng.load_dataset_device(d_raw.data_ptr(), nv, A, U)
         eng.set_folds(F, fos)
-        shard.run(order, h.SUBSET_TRAINING, total)     # search [-> all-gather -> merge]
+        if world == 1 or not record:
+            shard.run(order, h.SUBSET_TRAINING, total)     # search [-> all-gather -> merge]
+            return
+        # the same calls as ShardedSearch.run, with events between them (where a multi-GPU step spends its time)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        eng.search_device(order, h.SUBSET_TRAINING, RANK_SIZE, first, last, d_local.data_ptr())
+        e[0].record(stream)
+        sharding.all_gather_models(dist, d_local, world, out=d_all)
+        e[1].record(stream)
+        eng.merge_device(order, h.SUBSET_TRAINING, world, RANK_SIZE, d_all.data_ptr(), d_final.data_ptr())
+        e[2].record(stream)
+        phase_ev.append(e)
 
     def barrier():
         torch.cuda.synchronize()
@@ -280,33 +302,46 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
 
     # ---- timed region: K steps, CUDA events per step, L2 flushed between steps ----
-    sampler = ClockSampler(local_rank)
     launches0 = eng.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     search_ms = []
     barrier()
-    sampler.start()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         flush.fill_(k & 0xFF)                 # > L2 (126 MB): next step starts with a cold L2
         ev[k][0].record(stream)
-        step_device()
+        step_device(record=True)
         ev[k][1].record(stream)
     barrier()
     search_ms = eng.search_times(min(args.steps, 32))      # the library's CUDA events around each search launch
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_wall0, t_wall0 + t_wall)
     launches = eng.launch_count - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
+    phases = None
+    if world > 1 and phase_ev:
+        # per-rank means: pack + search, wait for the slowest rank + all-gather, final merge; search kernel alone
+        p = [np.mean([ev[k][0].elapsed_time(phase_ev[k][0]) for k in range(args.steps)]),
+             np.mean([phase_ev[k][0].elapsed_time(phase_ev[k][1]) for k in range(args.steps)]),
+             np.mean([phase_ev[k][1].elapsed_time(phase_ev[k][2]) for k in range(args.steps)]),
+             float(np.mean(search_ms))]
+        tmax = torch.tensor(p, dtype=torch.float64, device="cuda")
+        tmin = tmax.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        names = ["pack+search", "all_gather(incl. wait for the slowest rank)", "merge", "search_kernel"]
+        phases = {n: {"min_over_ranks": float(a), "max_over_ranks": float(b)} for n, a, b in zip(names, tmin.tolist(), tmax.tolist())}
     value = total * F * args.steps / (dev_ms * 1e-3)
 
     # ---- e2e: host buffers in, host result out ----
@@ -380,6 +415,8 @@ def main():
             "roofline": roofline,
             "wall_s_timed_region": t_wall,
         }
+        if phases:
+            line["phases_ms"] = phases
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

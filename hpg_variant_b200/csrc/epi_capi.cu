@@ -80,6 +80,8 @@ struct hpgv_epi_ctx {
     DevBuf<int> d_hist, d_hmax;
     DevBuf<int64_t> d_prefix;
     DevBuf<int32_t> d_jt0;
+    DevBuf<int2> d_unit_desc;
+    bool wl_has_desc = false;
     DevBuf<hpgv_epi_model_t> d_out;
     DevBuf<Cand> d_merge_in;
     // cached work list
@@ -171,7 +173,7 @@ extern "C" void hpgv_epi_destroy(hpgv_epi_ctx *ctx) {
     cudaSetDevice(ctx->device);
     ctx->raw_owned.release(); ctx->d_fl.release(); ctx->d_perm.release(); ctx->d_blk.release(); ctx->d_planes.release();
     ctx->d_lists.release(); ctx->d_list_cnt.release(); ctx->d_gthr.release(); ctx->d_hist.release(); ctx->d_hmax.release();
-    ctx->d_prefix.release(); ctx->d_jt0.release(); ctx->d_out.release(); ctx->d_merge_in.release();
+    ctx->d_prefix.release(); ctx->d_jt0.release(); ctx->d_unit_desc.release(); ctx->d_out.release(); ctx->d_merge_in.release();
     for (int k = 0; k < hpgv_epi_ctx::kEvRing; k++) { if (ctx->ev0[k]) cudaEventDestroy(ctx->ev0[k]); if (ctx->ev1[k]) cudaEventDestroy(ctx->ev1[k]); }
     if (ctx->ev_stage) cudaEventDestroy(ctx->ev_stage);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -196,7 +198,7 @@ static int set_dims(hpgv_epi_ctx *ctx, int64_t nv, int A, int U) {
     if (A < 1 || U < 1) FAIL(HPGV_E_ARG, "need at least one affected and one unaffected sample");
     ctx->nv = nv; ctx->A = A; ctx->U = U;
     ctx->folds_set = false;
-    ctx->wl_nv = -1;
+    // (the cached work list is keyed by nv, order, tile height and range: it survives a reload of the same shape)
     return HPGV_OK;
 }
 
@@ -557,6 +559,19 @@ static int build_worklist(hpgv_epi_ctx *ctx, int order, int ti, uint64_t first, 
         }
     }
     if (prefix.empty()) { prefix.push_back(0); jt0.push_back(0); }
+    // order 2: the tile origins of every unit, while the list stays small (8 bytes per unit of 512..640 pairs)
+    std::vector<int2> desc;
+    ctx->wl_has_desc = false;
+    if (order == 2 && units > 0 && units <= (int64_t) 16 << 20) {
+        desc.reserve((size_t) units);
+        for (size_t t = 0; t < prefix.size(); t++) {
+            const int64_t n = (t + 1 < prefix.size() ? prefix[t + 1] : units) - prefix[t];
+            for (int64_t x = 0; x < n; x++) desc.push_back(make_int2((it0 + (int) t) * ti, (jt0[t] + (int) x) * kTileJ));
+        }
+        CK(ctx->d_unit_desc.reserve(desc.size()));
+        CK(cudaMemcpyAsync(ctx->d_unit_desc.p, desc.data(), desc.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->wl_has_desc = true;
+    }
     CK(ctx->d_prefix.reserve(prefix.size()));
     CK(ctx->d_jt0.reserve(jt0.size()));
     CK(cudaMemcpyAsync(ctx->d_prefix.p, prefix.data(), prefix.size() * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -694,6 +709,10 @@ static int do_search(hpgv_epi_ctx *ctx, int order, int eval_subset, int rank, ui
     if (rc) return rc;
     args.unit_prefix = ctx->d_prefix.p;
     args.unit_jt0 = ctx->d_jt0.p;
+    {
+        const char *ud = getenv("HPGV_UNIT_DESC");            // A/B switch: walk the prefix table instead
+        args.unit_desc = (ctx->wl_has_desc && !(ud && ud[0] == '0')) ? ctx->d_unit_desc.p : nullptr;
+    }
     args.it0 = ctx->wl_it0;
     args.n_it = ctx->wl_nit;
     args.num_units = ctx->wl_units;

@@ -206,6 +206,11 @@ struct __align__(16) SearchCtl {
     int tq[kMaxFolds];             // the same bound on sum_c max(0, trA - trU) (balanced pre-filter): ceil(thr / n_f)
     int lock[kMaxFolds];
     int cnt[kMaxFolds];
+    // the entry that ranks last in a FULL list, published under a sequence lock (odd = being written, 0 = list not full yet):
+    // offers that rank at or after it are dropped without taking the fold's lock (floods of candidates that tie with the bound)
+    int root_seq[kMaxFolds];
+    double root_ba[kMaxFolds];
+    int root_t[kMaxFolds][3];
     FoldLayout fl;
 };
 
@@ -289,6 +294,18 @@ __device__ __forceinline__ void warp_offer(SearchCtl *ctl, const SearchArgs &a, 
         if (new_root) {
             // the root ranks last: its score is the threshold an offer must reach from now on
             const Cand root = cand_load(list);
+            {
+                volatile int *seq = &ctl->root_seq[f];
+                const int s0 = *seq;
+                *seq = s0 + 1;                                   // odd: readers keep out
+                __threadfence_block();
+                *reinterpret_cast<volatile double *>(&ctl->root_ba[f]) = root.ba;
+                *reinterpret_cast<volatile int *>(&ctl->root_t[f][0]) = root.i;
+                *reinterpret_cast<volatile int *>(&ctl->root_t[f][1]) = root.j;
+                *reinterpret_cast<volatile int *>(&ctl->root_t[f][2]) = root.k;
+                __threadfence_block();
+                *seq = s0 + 2;
+            }
             const FoldLayout &fl = ctl->fl;
             const int npos = a.training ? fl.A - fl.a_in[f] : fl.a_in[f];
             const int nneg = a.training ? fl.U - fl.u_in[f] : fl.u_in[f];
@@ -309,6 +326,28 @@ __device__ __forceinline__ void offer_fold(SearchCtl *ctl, const SearchArgs &a, 
                                            int lane) {
     const long long thr = *reinterpret_cast<volatile long long *>(&ctl->thr[f]);
     unsigned want = __ballot_sync(0xffffffffu, valid && score >= thr);
+    if (!want) return;
+    {
+        // Lanes whose tuple ranks at or after the last entry of the CTA's full list cannot enter it: they drop out here, in
+        // parallel and without the lock (a strong single SNP puts thousands of pairs on exactly the same score).  The
+        // snapshot is only used when the sequence number is even and unchanged around the reads; a stale root ranks at or
+        // after the current one, so it only lets more lanes through.
+        const volatile int *seq = &ctl->root_seq[f];
+        const int s0 = *seq;
+        if (s0 > 0 && !(s0 & 1)) {
+            __threadfence_block();
+            const double rb = *reinterpret_cast<const volatile double *>(&ctl->root_ba[f]);
+            const int ri = *reinterpret_cast<const volatile int *>(&ctl->root_t[f][0]);
+            const int rj = *reinterpret_cast<const volatile int *>(&ctl->root_t[f][1]);
+            const int rk = *reinterpret_cast<const volatile int *>(&ctl->root_t[f][2]);
+            __threadfence_block();
+            if (*seq == s0) {
+                const bool in = (want >> lane) & 1u;
+                const double my_ba = degenerate ? -INFINITY : balanced_accuracy(tp, fp, npos, nneg);
+                want = __ballot_sync(0xffffffffu, in && cand_before(my_ba, si, sj, sk, rb, ri, rj, rk));
+            }
+        }
+    }
     while (want) {
         // the threshold rises while the warp works through its lanes: drop the lanes that no longer reach it
         const long long now = *reinterpret_cast<volatile long long *>(&ctl->thr[f]);
@@ -782,7 +821,7 @@ __device__ __forceinline__ void search_init(SearchCtl *ctl, const SearchArgs &a,
         ctl->fl = *a.fl;
     }
     if (tid < kMaxFolds) {
-        ctl->thr[tid] = LLONG_MIN; ctl->lock[tid] = 0; ctl->cnt[tid] = 0;
+        ctl->thr[tid] = LLONG_MIN; ctl->lock[tid] = 0; ctl->cnt[tid] = 0; ctl->root_seq[tid] = 0;
         ctl->tq[tid] = tid < a.fl->F ? INT_MIN : INT_MAX;      // folds past F (odd F, byte-counter pairs) never pass
     }
     for (size_t x = tid; x < cnt_words; x += blockDim.x) cnt_base[x] = 0;   // halves that are never written must read 0
@@ -831,7 +870,16 @@ __global__ void __launch_bounds__((SINGLE ? kTriWarps : kMaxWarps) * 32, 1) sear
     // ---- step sequencing (thread 0): units blockIdx.x, blockIdx.x + gridDim.x, ... each cut into nchunks steps ----
     long long u = blockIdx.x;
     int grp = 0, chunk = 0, cur_i0 = 0, cur_j0 = 0;
+    int2 pre = make_int2(0, 0);                     // descriptor of unit pre_u, loaded one unit ahead
+    long long pre_u = -1;
     auto decode = [&]() {
+        if (a.unit_desc) {
+            const int2 d = pre_u == u ? pre : __ldg(a.unit_desc + u);
+            cur_i0 = d.x; cur_j0 = d.y;
+            pre_u = u + gridDim.x;
+            if (pre_u < a.num_units) pre = __ldg(a.unit_desc + pre_u);     // lands while the CTA counts
+            return;
+        }
         while (grp + 1 < a.n_it && a.unit_prefix[grp + 1] <= u) grp++;
         cur_i0 = (a.it0 + grp) * TI;
         cur_j0 = (a.unit_jt0[grp] + (int) (u - a.unit_prefix[grp])) * kTileJ;

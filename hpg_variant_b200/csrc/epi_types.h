@@ -1,6 +1,7 @@
 // epi_types.h -- structures shared by host and device code of the epistasis engine.
 #pragma once
 #include <stdint.h>
+#include <cuda_runtime.h>
 
 namespace hpgv {
 
@@ -83,6 +84,8 @@ struct SearchArgs {
     // work list: order 2 -> unit = (i-tile, j-tile); order 3 -> unit = (i, j-tile); prefix[t] = units before row-group t
     const int64_t *unit_prefix;
     const int32_t *unit_jt0;    // first j-tile of each row group
+    const int2 *unit_desc;      // order 2, when the list fits: tile origin (i0, j0) of every unit -- one load instead of a walk through
+                                // the prefix table (whose dependent loads sat on the critical path of the producer warp)
     int it0, n_it;              // first row group, number of row groups
     int64_t num_units;
     // per-CTA candidate lists
