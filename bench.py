@@ -380,7 +380,7 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     # DRAM bytes of one search launch from the committed `ncu --set full` capture of the same command (profiles/)
-    ncu_traffic = {"c2": {"bytes": 8591872 + 2304, "source": "profiles/r01d_search2_c2_ncu_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum)"}}
+    ncu_traffic = {"c2": {"bytes": 9217536 + 5120, "source": "profiles/r01e_search2_c2_ncu_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum)"}}
     tr = ncu_traffic.get(args.workload) if (world == 1 and not args.snps) else None
     roofline = {
         "bound": "int_popc", "kernel": f"search{order}_kernel", "achieved": achieved / 1e12, "peak": popc_peak / 1e12, "unit": "TPOPC32/s",

@@ -562,7 +562,7 @@ static int build_worklist(hpgv_epi_ctx *ctx, int order, int ti, uint64_t first, 
     // order 2: the tile origins of every unit, while the list stays small (8 bytes per unit of 512..640 pairs)
     std::vector<int2> desc;
     ctx->wl_has_desc = false;
-    if (order == 2 && units > 0 && units <= (int64_t) 16 << 20) {
+    if (order == 2 && units > 0 && units <= (int64_t) 2 << 20) {
         desc.reserve((size_t) units);
         for (size_t t = 0; t < prefix.size(); t++) {
             const int64_t n = (t + 1 < prefix.size() ? prefix[t + 1] : units) - prefix[t];

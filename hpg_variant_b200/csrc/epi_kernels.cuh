@@ -294,6 +294,7 @@ __device__ __forceinline__ void warp_offer(SearchCtl *ctl, const SearchArgs &a, 
         if (new_root) {
             // the root ranks last: its score is the threshold an offer must reach from now on
             const Cand root = cand_load(list);
+#ifndef HPGV_NO_ROOT_FILTER
             {
                 volatile int *seq = &ctl->root_seq[f];
                 const int s0 = *seq;
@@ -306,6 +307,7 @@ __device__ __forceinline__ void warp_offer(SearchCtl *ctl, const SearchArgs &a, 
                 __threadfence_block();
                 *seq = s0 + 2;
             }
+#endif
             const FoldLayout &fl = ctl->fl;
             const int npos = a.training ? fl.A - fl.a_in[f] : fl.a_in[f];
             const int nneg = a.training ? fl.U - fl.u_in[f] : fl.u_in[f];
@@ -327,6 +329,7 @@ __device__ __forceinline__ void offer_fold(SearchCtl *ctl, const SearchArgs &a, 
     const long long thr = *reinterpret_cast<volatile long long *>(&ctl->thr[f]);
     unsigned want = __ballot_sync(0xffffffffu, valid && score >= thr);
     if (!want) return;
+#ifndef HPGV_NO_ROOT_FILTER
     {
         // Lanes whose tuple ranks at or after the last entry of the CTA's full list cannot enter it: they drop out here, in
         // parallel and without the lock (a strong single SNP puts thousands of pairs on exactly the same score).  The
@@ -348,6 +351,7 @@ __device__ __forceinline__ void offer_fold(SearchCtl *ctl, const SearchArgs &a, 
             }
         }
     }
+#endif
     while (want) {
         // the threshold rises while the warp works through its lanes: drop the lanes that no longer reach it
         const long long now = *reinterpret_cast<volatile long long *>(&ctl->thr[f]);

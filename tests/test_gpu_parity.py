@@ -182,6 +182,25 @@ def test_histogram_thresholds_do_not_change_results(engine, monkeypatch, nv, A, 
     assert np.array_equal(ev["conf"][:, 0], with_hist["conf"][0, :8])
 
 
+@pytest.mark.parametrize("switch", ["HPGV_UNIT_DESC=0", "HPGV_TRI_DERIVE=0", "HPGV_TRI_WARPS=16", "HPGV_STAGES=2", "HPGV_STAGGER=0", "HPGV_PACK_WARP=1"])
+def test_development_switches_do_not_change_results(engine, monkeypatch, switch):
+    """Every A/B switch of the library selects another route to the same bytes (prefix-table walk instead of the per-unit
+    descriptors, every cell counted directly, 16 warps, two stages, no stagger, the one-warp-per-word packer)."""
+    nv, A, F, rank = 1200, 2000, 10, 40           # c3-shaped samples: 8-word single-block layout with marginals
+    g = synth.make_dataset(nv, A, A, seed=99, missing=0.01, planted=2)
+    fos, _ = h.k_folds(A, A, F, seed=3)
+    total = h.num_combinations(nv, 2)
+    engine.load_dataset(g, A, A)
+    engine.set_folds(F, fos)
+    want = [engine.search(2, h.SUBSET_TRAINING, rank), engine.search(2, h.SUBSET_TESTING, rank, total // 3, total)]
+    k, v = switch.split("=")
+    monkeypatch.setenv(k, v)
+    engine.set_folds(F, fos)
+    got = [engine.search(2, h.SUBSET_TRAINING, rank), engine.search(2, h.SUBSET_TESTING, rank, total // 3, total)]
+    for a, b in zip(want, got):
+        assert a.tobytes() == b.tobytes()
+
+
 def test_tri_layout_equals_four_word_layout(engine, monkeypatch):
     """The tri layout (3 words + shared 4-bit tails, 2 POPC per block) and the plain 4-word layout give the same bytes."""
     nv, A, U, F, rank = 150, 1000, 1000, 10, 50
