@@ -85,7 +85,10 @@ int hpgv_epi_dataset_dims(const hpgv_epi_ctx *ctx, int64_t *num_variants, int *n
 /* ---- folds: replaces get_k_folds_masks (cross_validation.c:102-132) and the
  * per-combination set_genotypes_masks (model.c:28-74).  fold_of_sample[s] in
  * [0, num_folds) is the fold whose TESTING part holds sample s (s in dataset
- * column order).  Builds the (class, fold)-segmented bit planes on the GPU. */
+ * column order).  Builds the (class, fold)-segmented bit planes on the GPU.
+ * Asynchronous on the context's stream: the call returns once the pack kernel is
+ * enqueued (fold_of_sample is copied before it returns); errors of the kernel
+ * surface at the next synchronising call. */
 int hpgv_epi_set_folds(hpgv_epi_ctx *ctx, int num_folds, const int32_t *fold_of_sample);
 
 /* Stratified k-fold assignment with the reference's algorithm
@@ -146,7 +149,8 @@ int hpgv_epi_run_host(hpgv_epi_ctx *ctx, const uint8_t *genotypes, int64_t num_v
 
 /* Introspection for benches/docs: layout chosen by set_folds. */
 typedef struct {
-    int num_folds, num_segments, num_blocks, block_words;   /* block = block_words 32-bit words of one (class, fold) segment */
+    int num_folds, num_segments, num_blocks, block_words;   /* block = block_words 32-bit words of one (class, fold) segment;
+                                                              * 3 = tri layout: three words plus a 4-bit tail shared eight to a word */
     int count_bits;                                          /* 8 or 16: per-segment counter width in shared memory */
     int64_t plane_bytes;                                     /* bytes of the packed planes in HBM */
     int words_per_class_row;                                 /* W of SURVEY 8(d): ceil(A/32)+ceil(U/32) */
