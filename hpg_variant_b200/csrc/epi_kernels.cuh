@@ -1,6 +1,8 @@
 // epi_kernels.cuh -- CUDA kernels of the epistasis engine (sm_100a).
 //
-//   pack_planes_kernel   bytes -> (fold, class)-segmented bit planes          (replaces set_genotypes_masks + get_k_folds_masks)
+//   pack_rows_kernel     bytes -> (fold, class)-segmented bit planes, staged through shared memory, with the per-block
+//                        marginals and missing masks of the byte-counter layouts  (replaces set_genotypes_masks + get_k_folds_masks)
+//   pack_planes_kernel   the same, one warp per word with gathered global loads (sample axes too long for shared memory)
 //   search2_kernel       exhaustive order-2 MDR: counts, risk, BA, top-N      (replaces process_set_of_combinations)
 //   search3_kernel       same for order 3
 //   merge_kernel         per-CTA / per-rank top-N lists -> final top-N        (replaces the heap drain + MPI tree merge)
@@ -22,6 +24,12 @@
 // / once per segment.  After the last chunk the thread derives, per fold, the
 // training table (total - in-fold), the exact high-risk mask, TP/FP and an integer
 // score, and offers tuples that beat the running threshold to the CTA's top-N list.
+//
+// Three things keep the order-2 kernels off the obvious costs: (1) in a block where SNP i has no missing sample the cells
+// of its genotype 2 follow from SNP j's own counts and the cells of genotypes 0 and 1 (derive_row2), so a third of the
+// AND/POPC work is skipped in most blocks; (2) the tri layout packs segments of <= 100 samples as three words plus a 4-bit
+// tail, 2 POPCs per block instead of 3; (3) a global histogram of pre-filter scores gives every CTA the bound of ALL pairs
+// seen so far (hist_threshold), so the per-CTA lists see a few thousand offers per search instead of half a million.
 #pragma once
 #include <type_traits>
 #include "epi_device.cuh"
