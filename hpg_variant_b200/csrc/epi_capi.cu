@@ -698,6 +698,8 @@ static int do_search(hpgv_epi_ctx *ctx, int order, int eval_subset, int rank, ui
     {
         const char *st = getenv("HPGV_STAGGER");
         args.stagger = st && st[0] >= '0' && st[0] <= '2' ? st[0] - '0' : 1;
+        const char *ls = getenv("HPGV_LIST_SCAN");
+        args.list_scan = (ls && ls[0] == '0') ? 0 : 1;        // default on; "0" keeps the heap for every list length
         const char *td = getenv("HPGV_TRI_DERIVE");
         args.tri_derive = !(td && td[0] == '0');
     }

@@ -216,6 +216,7 @@ struct __align__(16) SearchCtl {
     int cnt[kMaxFolds];
     // the entry that ranks last in a FULL list, published under a sequence lock (odd = being written, 0 = list not full yet):
     // offers that rank at or after it are dropped without taking the fold's lock (floods of candidates that tie with the bound)
+    int worst[kMaxFolds];          // array lists (offer_batch_scan): position of the entry that ranks last, once the list is full
     int root_seq[kMaxFolds];
     double root_ba[kMaxFolds];
     int root_t[kMaxFolds][3];
@@ -275,6 +276,27 @@ __device__ __forceinline__ void heap_sift_down(Cand *list, int n, int i, const C
     cand_store(list + i, c);
 }
 
+// publish the entry that ranks last in a full list: sequence-locked copy for the lock-free pre-check, score bounds
+__device__ __forceinline__ void publish_root(SearchCtl *ctl, const SearchArgs &a, int f, double ba, int i, int j, int k, int tp, int fp) {
+    volatile int *seq = &ctl->root_seq[f];
+    const int s0 = *seq;
+    *seq = s0 + 1;                                   // odd: readers keep out
+    __threadfence_block();
+    *reinterpret_cast<volatile double *>(&ctl->root_ba[f]) = ba;
+    *reinterpret_cast<volatile int *>(&ctl->root_t[f][0]) = i;
+    *reinterpret_cast<volatile int *>(&ctl->root_t[f][1]) = j;
+    *reinterpret_cast<volatile int *>(&ctl->root_t[f][2]) = k;
+    __threadfence_block();
+    *seq = s0 + 2;
+    const FoldLayout &fl = ctl->fl;
+    const int npos = a.training ? fl.A - fl.a_in[f] : fl.a_in[f];
+    const int nneg = a.training ? fl.U - fl.u_in[f] : fl.u_in[f];
+    const long long sc = (npos == 0 || nneg == 0) ? LLONG_MIN : ba_score(tp, fp, npos, nneg);
+    atomicMax(&ctl->thr[f], sc);
+    atomicMax(&ctl->tq[f], thr_quotient(sc, npos));
+    atomicMax(a.gthr + f, sc);
+}
+
 __device__ __forceinline__ void warp_offer(SearchCtl *ctl, const SearchArgs &a, Cand *lists, int f, const Cand &c, int lane) {
     if (lane == 0) {
         while (atomicCAS(&ctl->lock[f], 0, 1) != 0) __nanosleep(20);
@@ -302,27 +324,94 @@ __device__ __forceinline__ void warp_offer(SearchCtl *ctl, const SearchArgs &a, 
         if (new_root) {
             // the root ranks last: its score is the threshold an offer must reach from now on
             const Cand root = cand_load(list);
-#ifndef HPGV_NO_ROOT_FILTER
-            {
-                volatile int *seq = &ctl->root_seq[f];
-                const int s0 = *seq;
-                *seq = s0 + 1;                                   // odd: readers keep out
-                __threadfence_block();
-                *reinterpret_cast<volatile double *>(&ctl->root_ba[f]) = root.ba;
-                *reinterpret_cast<volatile int *>(&ctl->root_t[f][0]) = root.i;
-                *reinterpret_cast<volatile int *>(&ctl->root_t[f][1]) = root.j;
-                *reinterpret_cast<volatile int *>(&ctl->root_t[f][2]) = root.k;
-                __threadfence_block();
-                *seq = s0 + 2;
-            }
-#endif
-            const FoldLayout &fl = ctl->fl;
-            const int npos = a.training ? fl.A - fl.a_in[f] : fl.a_in[f];
-            const int nneg = a.training ? fl.U - fl.u_in[f] : fl.u_in[f];
-            const long long sc = (npos == 0 || nneg == 0) ? LLONG_MIN : ba_score(root.tp, root.fp, npos, nneg);
-            atomicMax(&ctl->thr[f], sc);
-            atomicMax(&ctl->tq[f], thr_quotient(sc, npos));
-            atomicMax(a.gthr + f, sc);
+            publish_root(ctl, a, f, root.ba, root.i, root.j, root.k, root.tp, root.fp);
+        }
+        __threadfence_block();
+        atomicExch(&ctl->lock[f], 0);
+    }
+    __syncwarp();
+}
+
+// ---- short lists (N <= 64) as plain arrays ----------------------------------------
+// A strong single SNP puts thousands of pairs on exactly the same score; the bound cannot rise above it, so all of them
+// are offered, a whole warp of them at a time when the unit holds the SNP's own row.  For that case the warp takes the
+// fold's lock ONCE for all its candidates and keeps the list as a plain array: an accepted candidate overwrites the entry
+// that ranks last and all 32 lanes find the new last entry (two entries per lane, five shuffle rounds) instead of lane 0
+// sifting a heap with dependent loads.
+struct RootReg {                 // the entry that ranks last, in registers of every lane (warp-uniform)
+    double ba;
+    int i, j, k, tp, fp, idx;
+};
+__device__ __forceinline__ bool before4(double ba_a, int ia, int ja, int ka, double ba_b, int ib, int jb, int kb) {
+    return cand_before(ba_a, ia, ja, ka, ba_b, ib, jb, kb);
+}
+__device__ __forceinline__ RootReg scan_last(const Cand *list, int n, int lane) {
+    RootReg r;
+    r.ba = 0.0; r.i = r.j = r.k = r.tp = r.fp = 0; r.idx = -1;
+    for (int e = lane; e < n; e += 32) {
+        const Cand x = cand_load(list + e);
+        if (r.idx < 0 || before4(r.ba, r.i, r.j, r.k, x.ba, x.i, x.j, x.k)) {
+            r.ba = x.ba; r.i = x.i; r.j = x.j; r.k = x.k; r.tp = x.tp; r.fp = x.fp; r.idx = e;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const double oba = __shfl_xor_sync(0xffffffffu, r.ba, d);
+        const int oi = __shfl_xor_sync(0xffffffffu, r.i, d), oj = __shfl_xor_sync(0xffffffffu, r.j, d), ok = __shfl_xor_sync(0xffffffffu, r.k, d);
+        const int otp = __shfl_xor_sync(0xffffffffu, r.tp, d), ofp = __shfl_xor_sync(0xffffffffu, r.fp, d), oidx = __shfl_xor_sync(0xffffffffu, r.idx, d);
+        // tuples are unique within a fold: the order is strict, both partners keep the same entry
+        if (oidx >= 0 && (r.idx < 0 || before4(r.ba, r.i, r.j, r.k, oba, oi, oj, ok))) {
+            r.ba = oba; r.i = oi; r.j = oj; r.k = ok; r.tp = otp; r.fp = ofp; r.idx = oidx;
+        }
+    }
+    return r;
+}
+__device__ __forceinline__ void offer_batch_scan(SearchCtl *ctl, const SearchArgs &a, Cand *lists, int f, unsigned want, double my_ba,
+                                                 int si, int sj, int sk, uint32_t mask, int tp, int fp, int lane) {
+    Cand *list = lists + (size_t) f * a.rank;
+    if (lane == 0) {
+        while (atomicCAS(&ctl->lock[f], 0, 1) != 0) __nanosleep(20);
+    }
+    __syncwarp();
+    __threadfence_block();
+    int cnt = *reinterpret_cast<volatile int *>(&ctl->cnt[f]);
+    RootReg root;
+    root.ba = 0.0; root.i = root.j = root.k = root.tp = root.fp = 0; root.idx = -1;
+    if (cnt >= a.rank) {
+        root.idx = *reinterpret_cast<volatile int *>(&ctl->worst[f]);
+        const Cand x = cand_load(list + root.idx);
+        root.ba = x.ba; root.i = x.i; root.j = x.j; root.k = x.k; root.tp = x.tp; root.fp = x.fp;
+    }
+    bool changed = false;
+    while (want) {                                   // warp-uniform
+        const int src = __ffs(want) - 1;
+        want &= want - 1;
+        Cand c;
+        c.ba = __shfl_sync(0xffffffffu, my_ba, src);
+        c.i = __shfl_sync(0xffffffffu, si, src);
+        c.j = __shfl_sync(0xffffffffu, sj, src);
+        c.k = __shfl_sync(0xffffffffu, sk, src);
+        c.mask = __shfl_sync(0xffffffffu, mask, src);
+        c.tp = __shfl_sync(0xffffffffu, tp, src);
+        c.fp = __shfl_sync(0xffffffffu, fp, src);
+        int slot = -1;
+        if (cnt < a.rank) slot = cnt++;
+        else if (before4(c.ba, c.i, c.j, c.k, root.ba, root.i, root.j, root.k)) slot = root.idx;
+        if (slot < 0) continue;
+        if (lane == 0) cand_store(list + slot, c);
+        if (cnt >= a.rank) {                         // the list is full and has changed: find the entry that ranks last now
+            __threadfence_block();
+            __syncwarp();
+            root = scan_last(list, a.rank, lane);
+            __syncwarp();                            // every lane has read the list before lane 0 stores again
+            changed = true;
+        }
+    }
+    if (lane == 0) {
+        *reinterpret_cast<volatile int *>(&ctl->cnt[f]) = cnt;
+        if (changed) {
+            *reinterpret_cast<volatile int *>(&ctl->worst[f]) = root.idx;
+            publish_root(ctl, a, f, root.ba, root.i, root.j, root.k, root.tp, root.fp);
         }
         __threadfence_block();
         atomicExch(&ctl->lock[f], 0);
@@ -337,7 +426,7 @@ __device__ __forceinline__ void offer_fold(SearchCtl *ctl, const SearchArgs &a, 
     const long long thr = *reinterpret_cast<volatile long long *>(&ctl->thr[f]);
     unsigned want = __ballot_sync(0xffffffffu, valid && score >= thr);
     if (!want) return;
-#ifndef HPGV_NO_ROOT_FILTER
+    const double my_ba = ((want >> lane) & 1u) ? (degenerate ? -INFINITY : balanced_accuracy(tp, fp, npos, nneg)) : 0.0;
     {
         // Lanes whose tuple ranks at or after the last entry of the CTA's full list cannot enter it: they drop out here, in
         // parallel and without the lock (a strong single SNP puts thousands of pairs on exactly the same score).  The
@@ -354,12 +443,14 @@ __device__ __forceinline__ void offer_fold(SearchCtl *ctl, const SearchArgs &a, 
             __threadfence_block();
             if (*seq == s0) {
                 const bool in = (want >> lane) & 1u;
-                const double my_ba = degenerate ? -INFINITY : balanced_accuracy(tp, fp, npos, nneg);
                 want = __ballot_sync(0xffffffffu, in && cand_before(my_ba, si, sj, sk, rb, ri, rj, rk));
             }
         }
     }
-#endif
+    if (a.list_scan && a.rank <= 64) {
+        if (want) offer_batch_scan(ctl, a, lists, f, want, my_ba, si, sj, sk, mask, tp, fp, lane);
+        return;
+    }
     while (want) {
         // the threshold rises while the warp works through its lanes: drop the lanes that no longer reach it
         const long long now = *reinterpret_cast<volatile long long *>(&ctl->thr[f]);
@@ -374,7 +465,7 @@ __device__ __forceinline__ void offer_fold(SearchCtl *ctl, const SearchArgs &a, 
         c.mask = __shfl_sync(0xffffffffu, mask, src);
         c.tp = __shfl_sync(0xffffffffu, tp, src);
         c.fp = __shfl_sync(0xffffffffu, fp, src);
-        c.ba = degenerate ? -INFINITY : balanced_accuracy(c.tp, c.fp, npos, nneg);
+        c.ba = __shfl_sync(0xffffffffu, my_ba, src);
         warp_offer(ctl, a, lists, f, c, lane);
     }
 }

@@ -99,6 +99,7 @@ struct SearchArgs {
     int hist_bins;              // A + 1
     int use_hist;
     int tri_derive;             // derive genotype 2 of SNP i from SNP j's marginals in blocks where i has no missing sample (rows with marg)
+    int list_scan;              // short per-CTA lists (N <= 64) are plain arrays, one lock per warp and fold (offer_batch_scan); HPGV_LIST_SCAN
     int nstages;                // shared-memory stages of the search kernel's ring (2 or 3)
     int stagger;                // 1: half of each sub-partition's warps starts half a unit late, 2: evenly spread phases, 0: off (HPGV_STAGGER)
 };
