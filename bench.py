@@ -303,7 +303,8 @@ def main():
             torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:                                   # rank 0's GPU is the one whose clocks the line reports
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
