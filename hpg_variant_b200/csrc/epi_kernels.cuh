@@ -447,7 +447,7 @@ __device__ __forceinline__ void offer_fold(SearchCtl *ctl, const SearchArgs &a, 
             }
         }
     }
-    if (a.list_scan && a.rank <= 64) {
+    if (a.list_scan && a.rank <= 64 && a.lists_in_smem) {     // (lists in global memory keep the heap: fewer, dependent accesses)
         if (want) offer_batch_scan(ctl, a, lists, f, want, my_ba, si, sj, sk, mask, tp, fp, lane);
         return;
     }
