@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--snps", type=int, default=0, help="override the SNP count of the workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the post-run check of the returned models against the oracle")
     ap.add_argument("--strong", action="store_true", help="keep the total work fixed when N > 1")
     return ap.parse_args()
 

@@ -7,5 +7,6 @@ include/hpgv_epi.h) and the C host API mirroring the reference
 tests and bench.py.  Importing the engine requires the built library; there is
 no CPU fallback.
 """
-from ._lib import MODEL_DTYPE, SUBSET_TESTING, SUBSET_TRAINING, UINT64_MAX, HpgvError  # noqa: F401
+from ._lib import (EVAL_BA, EVAL_CA, EVAL_CA_TRUE, EVAL_GAMMA, EVAL_TAU_B, EVAL_WBA, MODEL_DTYPE, SUBSET_TESTING,  # noqa: F401
+                   SUBSET_TRAINING, UINT64_MAX, HpgvError)
 from .engine import EpistasisEngine, k_folds, num_combinations  # noqa: F401

@@ -13,6 +13,8 @@ MODEL_DTYPE = np.dtype([("accuracy", "<f8"), ("snp", "<i4", (3,)), ("risky_mask"
 assert MODEL_DTYPE.itemsize == 40
 
 SUBSET_TESTING, SUBSET_TRAINING = 0, 1
+# enum eval_function (model.h:84) + the documented CA formula as an extension (include/hpgv_epi.h)
+EVAL_CA, EVAL_BA, EVAL_WBA, EVAL_GAMMA, EVAL_TAU_B, EVAL_CA_TRUE = 0, 1, 2, 3, 4, 5
 UINT64_MAX = (1 << 64) - 1
 
 
@@ -37,6 +39,8 @@ SYMBOLS = [
     "hpgv_epi_set_folds", "hpgv_epi_k_folds", "hpgv_epi_search", "hpgv_epi_search_device", "hpgv_epi_merge_device",
     "hpgv_epi_num_combinations", "hpgv_epi_eval", "hpgv_epi_unpack_masks", "hpgv_epi_run_host", "hpgv_epi_layout",
     "hpgv_epi_pipe_peak", "hpgv_epi_last_search_ms", "hpgv_epi_search_times",
+    "hpgv_epi_set_eval_function", "hpgv_epi_confusion", "hpgv_epi_high_risk", "hpgv_epi_evaluate",
+    "hpgv_epi_debug_counters",
 ]
 
 
@@ -76,5 +80,10 @@ def load():
     lib.hpgv_epi_last_search_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i32)]
     lib.hpgv_epi_search_times.argtypes = [vp, i32, C.POINTER(C.c_float)]
     lib.hpgv_epi_pipe_peak.argtypes = [vp, i32, i32, C.POINTER(C.c_double)]
+    lib.hpgv_epi_set_eval_function.argtypes = [vp, i32]
+    lib.hpgv_epi_confusion.argtypes = [vp, i32, i32, i64, vp, vp, vp, vp]
+    lib.hpgv_epi_high_risk.argtypes = [vp, vp, vp, i64, i32, i32, vp]
+    lib.hpgv_epi_evaluate.argtypes = [vp, i32, i64, vp, vp]
+    lib.hpgv_epi_debug_counters.argtypes = [vp, vp, i32]
     _lib = lib
     return lib

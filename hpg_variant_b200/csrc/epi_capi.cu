@@ -51,6 +51,7 @@ struct hpgv_epi_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     int64_t launches = 0;
+    int eval_fn = kEvalBA;                // what ranks the models (hpgv_epi_set_eval_function); BA like the reference runner (model.c:331)
 
     // dataset
     const uint8_t *d_raw = nullptr;
@@ -78,6 +79,7 @@ struct hpgv_epi_ctx {
     DevBuf<int> d_list_cnt;
     DevBuf<long long> d_gthr;
     DevBuf<int> d_hist, d_hmax;
+    DevBuf<unsigned long long> d_dbg;     // development counters (HPGV_DEBUG_COUNTERS=1)
     DevBuf<int64_t> d_prefix;
     DevBuf<int32_t> d_jt0;
     DevBuf<int2> d_unit_desc;
@@ -121,8 +123,9 @@ struct hpgv_epi_ctx {
 // ---------------------------------------------------------------------------------
 // reset kernel: global thresholds
 // ---------------------------------------------------------------------------------
-__global__ void reset_search_kernel(long long *gthr, int *ghmax) {
+__global__ void reset_search_kernel(long long *gthr, int *ghmax) {      // ghmax[kMaxFolds] = SearchArgs::gfirst
     if (threadIdx.x < kMaxFolds) { gthr[threadIdx.x] = LLONG_MIN; ghmax[threadIdx.x] = -1; }
+    if (threadIdx.x == 0) ghmax[kMaxFolds] = 0;
 }
 
 // ---------------------------------------------------------------------------------
@@ -172,7 +175,7 @@ extern "C" void hpgv_epi_destroy(hpgv_epi_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     ctx->raw_owned.release(); ctx->d_fl.release(); ctx->d_perm.release(); ctx->d_blk.release(); ctx->d_planes.release();
-    ctx->d_lists.release(); ctx->d_list_cnt.release(); ctx->d_gthr.release(); ctx->d_hist.release(); ctx->d_hmax.release();
+    ctx->d_lists.release(); ctx->d_list_cnt.release(); ctx->d_gthr.release(); ctx->d_hist.release(); ctx->d_hmax.release(); ctx->d_dbg.release();
     ctx->d_prefix.release(); ctx->d_jt0.release(); ctx->d_unit_desc.release(); ctx->d_out.release(); ctx->d_merge_in.release();
     for (int k = 0; k < hpgv_epi_ctx::kEvRing; k++) { if (ctx->ev0[k]) cudaEventDestroy(ctx->ev0[k]); if (ctx->ev1[k]) cudaEventDestroy(ctx->ev1[k]); }
     if (ctx->ev_stage) cudaEventDestroy(ctx->ev_stage);
@@ -189,6 +192,14 @@ extern "C" int hpgv_epi_set_stream(hpgv_epi_ctx *ctx, void *cuda_stream) {
 }
 
 extern "C" int64_t hpgv_epi_launch_count(const hpgv_epi_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int hpgv_epi_set_eval_function(hpgv_epi_ctx *ctx, int eval_function) {
+    if (!ctx) return HPGV_E_ARG;
+    if (eval_function == HPGV_EVAL_WBA) FAIL(HPGV_E_UNSUPPORTED, "wBA is declared but not implemented by the reference (model.h:84, no case in model.c:469-478)");
+    if (eval_function < HPGV_EVAL_CA || eval_function > HPGV_EVAL_CA_TRUE) FAIL(HPGV_E_ARG, "unknown evaluation function");
+    ctx->eval_fn = eval_function;
+    return HPGV_OK;
+}
 
 // ---------------------------------------------------------------------------------
 // dataset
@@ -624,11 +635,27 @@ static int launch_search(hpgv_epi_ctx *ctx, K kernel, const SearchShape &shape, 
     CK(ctx->d_lists.reserve((size_t) grid * F * rank));
     CK(ctx->d_list_cnt.reserve((size_t) grid * F));
     CK(ctx->d_gthr.reserve(kMaxFolds));
-    CK(ctx->d_hmax.reserve(kMaxFolds));
+    CK(ctx->d_hmax.reserve(kMaxFolds + 1));
+    args.dbg = nullptr;
+    {
+        const char *dc = getenv("HPGV_DEBUG_COUNTERS");
+        if (dc && dc[0] == '1') {
+            CK(ctx->d_dbg.reserve(kDbgWords));
+            CK(cudaMemsetAsync(ctx->d_dbg.p, 0, (kDbgTrace + 8) * sizeof(unsigned long long), ctx->stream));
+            args.dbg = ctx->d_dbg.p;
+        }
+    }
+    {
+        const char *fb = getenv("HPGV_FRESH_BOUND");          // A/B switch: "1" = adopt other CTAs' published bounds once per unit
+        args.fresh_bound = (fb && fb[0] == '1') ? 1 : 0;       // measured: costs 2 % and buys nothing once the start-up race is gone
+        const char *fw = getenv("HPGV_FIRST_WAIT");
+        args.first_wait = (fw && fw[0] == '0') ? 0 : 1;
+    }
     args.lists = ctx->d_lists.p;
     args.list_cnt = ctx->d_list_cnt.p;
     args.gthr = ctx->d_gthr.p;
     args.ghmax = ctx->d_hmax.p;
+    args.gfirst = ctx->d_hmax.p + kMaxFolds;
     args.ghist = nullptr;
     if (args.use_hist) {
         const size_t bins = (size_t) F * (args.hist_bins + hist_coarse_bins(args.hist_bins));
@@ -723,10 +750,13 @@ static int do_search(hpgv_epi_ctx *ctx, int order, int eval_subset, int rank, ui
 
     // the packed-pair epilogue needs A == U (r = 1: the float32 rule is exact) and 16-bit class sizes
     const bool balanced = fl.balanced && fl.A <= 65535;
+    args.eval_fn = ctx->eval_fn == kEvalCA ? kEvalBA : ctx->eval_fn;      // the reference turns code 0 into BA (model.c:465-467)
     {
-        // score histogram: the pre-filter's conditions (epilogue_balanced_t) and the order-2 kernel's step modes
+        // the balanced pre-filter (epilogue_balanced_t) orders by TP - FP: BA on the TRAINING part of equal folds only
+        args.prefilter = (balanced && fl.eqfolds && args.training && args.eval_fn == kEvalBA) ? 1 : 0;
+        // score histogram: the pre-filter's conditions and the order-2 kernel's step modes
         const char *hs = getenv("HPGV_HIST");
-        args.use_hist = (order == 2 && balanced && fl.eqfolds && args.training && !(hs && hs[0] == '0')) ? 1 : 0;
+        args.use_hist = (order == 2 && args.prefilter && !(hs && hs[0] == '0')) ? 1 : 0;
         args.hist_bins = fl.A + 1;
     }
     int grid = 0;
@@ -802,8 +832,8 @@ extern "C" int hpgv_epi_merge_device(hpgv_epi_ctx *ctx, int order, int eval_subs
 // ---------------------------------------------------------------------------------
 // parity hooks
 // ---------------------------------------------------------------------------------
-extern "C" int hpgv_epi_eval(hpgv_epi_ctx *ctx, int order, int eval_subset, int64_t ncomb, const int32_t *combs,
-                             int32_t *counts_aff, int32_t *counts_unaff, uint32_t *risky_mask, uint32_t *conf, double *accuracy) {
+static int eval_impl(hpgv_epi_ctx *ctx, int order, int eval_subset, int64_t ncomb, const int32_t *combs, const uint32_t *risky_in,
+                     int32_t *counts_aff, int32_t *counts_unaff, uint32_t *risky_mask, uint32_t *conf, double *accuracy) {
     if (!ctx || !combs || ncomb < 0) return HPGV_E_ARG;
     if (!ctx->folds_set) FAIL(HPGV_E_STATE, "eval before set_folds");
     if (order != 2 && order != 3) FAIL(HPGV_E_ARG, "order must be 2 or 3");
@@ -814,13 +844,13 @@ extern "C" int hpgv_epi_eval(hpgv_epi_ctx *ctx, int order, int eval_subset, int6
             if (v < 0 || v >= ctx->nv || (o > 0 && v <= combs[c * order + o - 1])) FAIL(HPGV_E_ARG, "combination indices must be ascending and inside the dataset");
         }
     CK(cudaSetDevice(ctx->device));
+    // the per-combination dump reads logical words: an order-3 dump of a tri-packed dataset is fine (logical_word serves every layout)
     const int F = ctx->fl.F, C = order == 2 ? 9 : 27;
     const size_t nf = (size_t) ncomb * F;
     int32_t *d_combs = nullptr, *d_ca = nullptr, *d_cu = nullptr;
-    uint32_t *d_mask = nullptr, *d_conf = nullptr;
+    uint32_t *d_mask = nullptr, *d_mask_in = nullptr, *d_conf = nullptr;
     double *d_acc = nullptr;
-    int rc = HPGV_OK;
-    auto cleanup = [&]() { cudaFree(d_combs); cudaFree(d_ca); cudaFree(d_cu); cudaFree(d_mask); cudaFree(d_conf); cudaFree(d_acc); };
+    auto cleanup = [&]() { cudaFree(d_combs); cudaFree(d_ca); cudaFree(d_cu); cudaFree(d_mask); cudaFree(d_mask_in); cudaFree(d_conf); cudaFree(d_acc); };
 #define CKE(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); cleanup(); return HPGV_E_CUDA; } } while (0)
     CKE(cudaMalloc(&d_combs, (size_t) ncomb * order * sizeof(int32_t)));
     CKE(cudaMalloc(&d_ca, nf * C * sizeof(int32_t)));
@@ -829,11 +859,17 @@ extern "C" int hpgv_epi_eval(hpgv_epi_ctx *ctx, int order, int eval_subset, int6
     CKE(cudaMalloc(&d_conf, nf * 4 * sizeof(uint32_t)));
     CKE(cudaMalloc(&d_acc, nf * sizeof(double)));
     CKE(cudaMemcpyAsync(d_combs, combs, (size_t) ncomb * order * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (risky_in) {
+        CKE(cudaMalloc(&d_mask_in, nf * sizeof(uint32_t)));
+        CKE(cudaMemcpyAsync(d_mask_in, risky_in, nf * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
     const int warps = 4;
     const size_t smem = (size_t) warps * ctx->fl.nseg * C * sizeof(int);
     const unsigned grid = (unsigned) ((ncomb + warps - 1) / warps);
     const int training = (eval_subset == HPGV_SUBSET_TRAINING);
-    eval_kernel<<<grid, warps * 32, smem, ctx->stream>>>(ctx->d_planes.p, ctx->d_blk.p, ctx->d_fl.p, ctx->snp_pad, order, training, ncomb, d_combs, d_ca, d_cu, d_mask, d_conf, d_acc);
+    eval_kernel<<<grid, warps * 32, smem, ctx->stream>>>(ctx->d_planes.p, ctx->d_blk.p, ctx->d_fl.p, ctx->snp_pad, order, training,
+                                                         ctx->eval_fn == kEvalCA ? kEvalBA : ctx->eval_fn, ncomb, d_combs, d_mask_in,
+                                                         d_ca, d_cu, d_mask, d_conf, d_acc);
     CKE(cudaGetLastError());
     ctx->launches++;
     if (counts_aff) CKE(cudaMemcpyAsync(counts_aff, d_ca, nf * C * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -844,7 +880,64 @@ extern "C" int hpgv_epi_eval(hpgv_epi_ctx *ctx, int order, int eval_subset, int6
     CKE(cudaStreamSynchronize(ctx->stream));
 #undef CKE
     cleanup();
-    return rc;
+    return HPGV_OK;
+}
+
+extern "C" int hpgv_epi_eval(hpgv_epi_ctx *ctx, int order, int eval_subset, int64_t ncomb, const int32_t *combs,
+                             int32_t *counts_aff, int32_t *counts_unaff, uint32_t *risky_mask, uint32_t *conf, double *accuracy) {
+    return eval_impl(ctx, order, eval_subset, ncomb, combs, nullptr, counts_aff, counts_unaff, risky_mask, conf, accuracy);
+}
+
+extern "C" int hpgv_epi_confusion(hpgv_epi_ctx *ctx, int order, int eval_subset, int64_t ncomb, const int32_t *combs,
+                                  const uint32_t *risky_mask_in, uint32_t *conf, double *accuracy) {
+    if (!risky_mask_in) return HPGV_E_ARG;
+    return eval_impl(ctx, order, eval_subset, ncomb, combs, risky_mask_in, nullptr, nullptr, nullptr, conf, accuracy);
+}
+
+// explicit count pairs / confusion matrices through the device functions the search kernels use
+extern "C" int hpgv_epi_high_risk(hpgv_epi_ctx *ctx, const int32_t *counts_aff, const int32_t *counts_unaff, int64_t n,
+                                  int num_affected, int num_unaffected, int32_t *flags) {
+    if (!ctx || !counts_aff || !counts_unaff || !flags || n < 0) return HPGV_E_ARG;
+    if (num_affected < 1 || num_unaffected < 1) FAIL(HPGV_E_ARG, "need at least one affected and one unaffected sample");
+    if (n == 0) return HPGV_OK;
+    CK(cudaSetDevice(ctx->device));
+    int32_t *d = nullptr;
+    CK(cudaMalloc(&d, (size_t) n * 3 * sizeof(int32_t)));
+    cudaError_t e = cudaMemcpyAsync(d, counts_aff, (size_t) n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + n, counts_unaff, (size_t) n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        high_risk_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(d, d + n, n, num_affected, num_unaffected, d + 2 * n);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(flags, d + 2 * n, (size_t) n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) FAIL(HPGV_E_CUDA, std::string("high_risk: ") + cudaGetErrorString(e));
+    return HPGV_OK;
+}
+
+extern "C" int hpgv_epi_evaluate(hpgv_epi_ctx *ctx, int eval_function, int64_t n, const uint32_t *conf, double *values) {
+    if (!ctx || !conf || !values || n < 0) return HPGV_E_ARG;
+    if (eval_function == HPGV_EVAL_WBA) FAIL(HPGV_E_UNSUPPORTED, "wBA is declared but not implemented by the reference (model.h:84)");
+    if (eval_function < HPGV_EVAL_CA || eval_function > HPGV_EVAL_CA_TRUE) FAIL(HPGV_E_ARG, "unknown evaluation function");
+    if (n == 0) return HPGV_OK;
+    CK(cudaSetDevice(ctx->device));
+    uint32_t *d_conf = nullptr;
+    double *d_val = nullptr;
+    CK(cudaMalloc(&d_conf, (size_t) n * 4 * sizeof(uint32_t)));
+    cudaError_t e = cudaMalloc(&d_val, (size_t) n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_conf, conf, (size_t) n * 4 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        evaluate_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(eval_function == kEvalCA ? kEvalBA : eval_function, n, d_conf, d_val);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(values, d_val, (size_t) n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_conf); cudaFree(d_val);
+    if (e != cudaSuccess) FAIL(HPGV_E_CUDA, std::string("evaluate: ") + cudaGetErrorString(e));
+    return HPGV_OK;
 }
 
 extern "C" int hpgv_epi_unpack_masks(hpgv_epi_ctx *ctx, int64_t variant, uint8_t *out) {
@@ -894,6 +987,16 @@ extern "C" int hpgv_epi_search_times(hpgv_epi_ctx *ctx, int n, float *ms) {
         CK(cudaEventSynchronize(ctx->ev1[slot]));
         CK(cudaEventElapsedTime(ms + k, ctx->ev0[slot], ctx->ev1[slot]));
     }
+    return n;
+}
+
+extern "C" int hpgv_epi_debug_counters(hpgv_epi_ctx *ctx, uint64_t *out, int n) {
+    if (!ctx || !out || n < 0) return HPGV_E_ARG;
+    if (!ctx->d_dbg.p) FAIL(HPGV_E_STATE, "no search has run with HPGV_DEBUG_COUNTERS=1");
+    n = std::min<int>(n, (int) ctx->d_dbg.cap);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(out, ctx->d_dbg.p, (size_t) n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return n;
 }
 

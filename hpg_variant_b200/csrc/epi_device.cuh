@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <limits.h>
 #include "epi_types.h"
 
 namespace hpgv {
@@ -263,6 +264,32 @@ __device__ __forceinline__ double balanced_accuracy(int tp, int fp, int npos, in
     double a = __ddiv_rn(TP, __dadd_rn(TP, FN));
     double b = __ddiv_rn(TN, __dadd_rn(TN, FP));
     return __dmul_rn(__dadd_rn(a, b), 0.5);   // /2 is exact
+}
+
+// The other evaluation functions of model.h:84 / model.c:462-479, from {TP, FN, FP, TN} in double, operation by operation
+// like the reference's C (gcc, no FMA contraction: every product and sum is rounded on its own).  Codes = enum eval_function
+// { CA, BA, wBA, GAMMA, TAU_B }.  CA (0) is what the reference EXECUTES for it: `if (!function) function = BA`
+// (model.c:465-467) turns code 0 into BA; kEvalCATrue is the documented formula as an extension.  wBA is a TODO in the
+// reference (no case in its switch) and is rejected on the host.
+constexpr int kEvalCA = 0, kEvalBA = 1, kEvalWBA = 2, kEvalGamma = 3, kEvalTauB = 4, kEvalCATrue = 5;
+__device__ __forceinline__ double evaluate_fn(int fn, int tp, int fn_, int fp, int tn) {
+    const double TP = (double) tp, FN = (double) fn_, FP = (double) fp, TN = (double) tn;
+    if (fn == kEvalGamma || fn == kEvalTauB) {
+        const double cross = __dsub_rn(__dmul_rn(TP, TN), __dmul_rn(FP, FN));
+        if (fn == kEvalGamma) return __ddiv_rn(cross, __dadd_rn(__dmul_rn(TP, TN), __dmul_rn(FP, FN)));
+        const double prod = __dmul_rn(__dmul_rn(__dmul_rn(__dadd_rn(TP, FN), __dadd_rn(TN, FP)), __dadd_rn(TP, FP)), __dadd_rn(TN, FN));
+        return __ddiv_rn(cross, __dsqrt_rn(prod));
+    }
+    if (fn == kEvalCATrue) return __ddiv_rn(__dadd_rn(TP, TN), __dadd_rn(__dadd_rn(__dadd_rn(TP, FN), TN), FP));
+    const double a = __ddiv_rn(TP, __dadd_rn(TP, FN));
+    const double b = __ddiv_rn(TN, __dadd_rn(TN, FP));
+    return __dmul_rn(__dadd_rn(a, b), 0.5);
+}
+// order-preserving integer image of a (non-NaN) double: the thresholds of the search are integer scores
+__device__ __forceinline__ long long value_score(double v) {
+    if (isnan(v)) return LLONG_MIN;
+    const long long b = __double_as_longlong(__dadd_rn(v, 0.0));     // -0.0 -> +0.0
+    return b ^ ((b >> 63) & 0x7FFFFFFFFFFFFFFFLL);
 }
 
 // Integer score with the same ordering as the real-valued BA for a fixed fold:

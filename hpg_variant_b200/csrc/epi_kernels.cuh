@@ -206,6 +206,23 @@ __global__ void unpack_masks_kernel(const uint32_t *__restrict__ planes, int64_t
 // ============================================================================
 // Shared pieces of the search kernels
 // ============================================================================
+// ---- 128-bit ranking keys ------------------------------------------------------
+// The canonical order (accuracy descending, then SNP tuple ascending) as "larger key first"; tuples are unique within a
+// fold, so keys are unique.  Used by the merge and by the global root below.
+// (struct Key128: epi_types.h)
+__device__ __forceinline__ bool key_ge(const Key128 &a, const Key128 &b) { return a.hi > b.hi || (a.hi == b.hi && a.lo >= b.lo); }
+__device__ __forceinline__ bool key_gt(const Key128 &a, const Key128 &b) { return a.hi > b.hi || (a.hi == b.hi && a.lo > b.lo); }
+__device__ __forceinline__ Key128 make_key(double ba, int i, int j, int k) {      // k < 0: order 2
+    Key128 key;
+    unsigned long long u = (unsigned long long) __double_as_longlong(ba);
+    key.hi = (u >> 63) ? ~u : (u | 0x8000000000000000ULL);           // larger accuracy -> larger key
+    unsigned long long t = k < 0 ? (((unsigned long long) (uint32_t) i << 32) | (uint32_t) j)
+                                 : (((unsigned long long) (uint32_t) i << 42) | ((unsigned long long) (uint32_t) j << 21) | (uint32_t) k);
+    key.lo = ~t;                                                      // smaller tuple -> larger key
+    return key;
+}
+__device__ __forceinline__ Key128 cand_key(const Cand &c, int order) { return make_key(c.ba, c.i, c.j, order == 2 ? -1 : c.k); }
+
 struct __align__(16) SearchCtl {
     uint64_t full[3];              // per stage (two or three are in use): the chunk rows have landed
     uint64_t empty[3];             // per stage: every warp is done reading it
@@ -220,6 +237,8 @@ struct __align__(16) SearchCtl {
     int root_seq[kMaxFolds];
     double root_ba[kMaxFolds];
     int root_t[kMaxFolds][3];
+    int first_best[kMaxFolds];     // best pre-filter score of the CTA's first unit, per fold (-1: none); see hist_count_tuple
+    int first_done;                // warps that are through with the CTA's first unit
     FoldLayout fl;
 };
 
@@ -291,7 +310,8 @@ __device__ __forceinline__ void publish_root(SearchCtl *ctl, const SearchArgs &a
     const FoldLayout &fl = ctl->fl;
     const int npos = a.training ? fl.A - fl.a_in[f] : fl.a_in[f];
     const int nneg = a.training ? fl.U - fl.u_in[f] : fl.u_in[f];
-    const long long sc = (npos == 0 || nneg == 0) ? LLONG_MIN : ba_score(tp, fp, npos, nneg);
+    const long long sc = (npos == 0 || nneg == 0) ? LLONG_MIN
+                         : (a.eval_fn == kEvalBA ? ba_score(tp, fp, npos, nneg) : value_score(evaluate_fn(a.eval_fn, tp, npos - tp, fp, nneg - fp)));
     atomicMax(&ctl->thr[f], sc);
     atomicMax(&ctl->tq[f], thr_quotient(sc, npos));
     atomicMax(a.gthr + f, sc);
@@ -366,11 +386,23 @@ __device__ __forceinline__ RootReg scan_last(const Cand *list, int n, int lane) 
     }
     return r;
 }
+__device__ __forceinline__ void dbg_add(const SearchArgs &a, int slot, unsigned long long v) {
+    if (a.dbg) atomicAdd(a.dbg + slot, v);
+}
+// development trace of the offered tuples: (i, j), (fold, score, bound); out of line so that it costs the kernels no registers
+__device__ __noinline__ void dbg_trace(unsigned long long *dbg, int si, int sj, int f, long long score, long long thr) {
+    const unsigned long long pos = atomicAdd(dbg + kDbgTraceCount, 1ULL);
+    if (pos >= kDbgTraceCap) return;
+    dbg[kDbgTrace + 2 * pos] = ((unsigned long long) (uint32_t) si << 32) | (uint32_t) sj;
+    dbg[kDbgTrace + 2 * pos + 1] = ((unsigned long long) f << 56) | ((unsigned long long) (score & 0xfffffff) << 28) | (unsigned long long) (thr & 0xfffffff);
+}
 __device__ __forceinline__ void offer_batch_scan(SearchCtl *ctl, const SearchArgs &a, Cand *lists, int f, unsigned want, double my_ba,
                                                  int si, int sj, int sk, uint32_t mask, int tp, int fp, int lane) {
     Cand *list = lists + (size_t) f * a.rank;
     if (lane == 0) {
-        while (atomicCAS(&ctl->lock[f], 0, 1) != 0) __nanosleep(20);
+        unsigned spins = 0;
+        while (atomicCAS(&ctl->lock[f], 0, 1) != 0) { __nanosleep(20); spins++; }
+        if (spins) dbg_add(a, 4, spins);
     }
     __syncwarp();
     __threadfence_block();
@@ -398,7 +430,7 @@ __device__ __forceinline__ void offer_batch_scan(SearchCtl *ctl, const SearchArg
         if (cnt < a.rank) slot = cnt++;
         else if (before4(c.ba, c.i, c.j, c.k, root.ba, root.i, root.j, root.k)) slot = root.idx;
         if (slot < 0) continue;
-        if (lane == 0) cand_store(list + slot, c);
+        if (lane == 0) { cand_store(list + slot, c); dbg_add(a, 3, 1); }
         if (cnt >= a.rank) {                         // the list is full and has changed: find the entry that ranks last now
             __threadfence_block();
             __syncwarp();
@@ -426,7 +458,19 @@ __device__ __forceinline__ void offer_fold(SearchCtl *ctl, const SearchArgs &a, 
     const long long thr = *reinterpret_cast<volatile long long *>(&ctl->thr[f]);
     unsigned want = __ballot_sync(0xffffffffu, valid && score >= thr);
     if (!want) return;
-    const double my_ba = ((want >> lane) & 1u) ? (degenerate ? -INFINITY : balanced_accuracy(tp, fp, npos, nneg)) : 0.0;
+    if (lane == 0) dbg_add(a, 1, __popc(want));
+#ifdef HPGV_DEV_TRACE                                  // development builds only (nvcc -DHPGV_DEV_TRACE): costs the kernels registers
+    if (a.dbg && ((want >> lane) & 1u)) dbg_trace(a.dbg, si, sj, f, score, thr);
+#endif
+    double my_ba = 0.0;
+    if ((want >> lane) & 1u) {
+        if (degenerate) my_ba = -INFINITY;
+        else if (a.eval_fn == kEvalBA) my_ba = balanced_accuracy(tp, fp, npos, nneg);
+        else {
+            my_ba = evaluate_fn(a.eval_fn, tp, npos - tp, fp, nneg - fp);
+            my_ba = isnan(my_ba) ? -INFINITY : __dadd_rn(my_ba, 0.0);        // NaN ranks last, like a degenerate fold
+        }
+    }
     {
         // Lanes whose tuple ranks at or after the last entry of the CTA's full list cannot enter it: they drop out here, in
         // parallel and without the lock (a strong single SNP puts thousands of pairs on exactly the same score).  The
@@ -447,6 +491,7 @@ __device__ __forceinline__ void offer_fold(SearchCtl *ctl, const SearchArgs &a, 
             }
         }
     }
+    if (lane == 0 && want) dbg_add(a, 2, __popc(want));
     if (a.list_scan && a.rank <= 64 && a.lists_in_smem) {     // (lists in global memory keep the heap: fewer, dependent accesses)
         if (want) offer_batch_scan(ctl, a, lists, f, want, my_ba, si, sj, sk, mask, tp, fp, lane);
         return;
@@ -518,7 +563,8 @@ __device__ __forceinline__ void epilogue_general(SearchCtl *ctl, const SearchArg
         const int npos = a.training ? fl.A - fl.a_in[f] : fl.a_in[f];
         const int nneg = a.training ? fl.U - fl.u_in[f] : fl.u_in[f];
         const bool degenerate = (npos == 0 || nneg == 0);   // BA = 0/0 = NaN in the reference (model.c:473)
-        const long long score = degenerate ? LLONG_MIN : ba_score(tp, fp, npos, nneg);
+        const long long score = degenerate ? LLONG_MIN
+                                : (a.eval_fn == kEvalBA ? ba_score(tp, fp, npos, nneg) : value_score(evaluate_fn(a.eval_fn, tp, npos - tp, fp, nneg - fp)));
         offer_fold(ctl, a, lists, f, valid, score, degenerate, npos, nneg, si, sj, sk, mask, tp, fp, lane);
     }
 }
@@ -572,7 +618,8 @@ __device__ __forceinline__ void balanced_fold(SearchCtl *ctl, const SearchArgs &
     const int npos = TRAINING ? fl.A - fl.a_in[f] : fl.a_in[f];
     const int nneg = TRAINING ? fl.U - fl.u_in[f] : fl.u_in[f];
     const bool degenerate = (npos == 0 || nneg == 0);
-    const long long score = degenerate ? LLONG_MIN : ba_score(tp, fp, npos, nneg);
+    const long long score = degenerate ? LLONG_MIN
+                            : (a.eval_fn == kEvalBA ? ba_score(tp, fp, npos, nneg) : value_score(evaluate_fn(a.eval_fn, tp, npos - tp, fp, nneg - fp)));
     offer_fold(ctl, a, lists, f, valid, score, degenerate, npos, nneg, si, sj, sk, mask, tp, fp, lane);
 }
 
@@ -635,7 +682,7 @@ constexpr int kModeCount = 1, kModeOffer = 2;
 // whole first unit of a CTA (all = true) and afterwards only for warps that hold a candidate: kept out of line so that
 // it costs the common path no registers.
 template <int NCELLS, bool U8>
-__device__ __noinline__ void hist_count_tuple(const SearchCtl *ctl, int *ghist, int *ghmax, int hist_bins, const uint32_t *cnts, int nwc,
+__device__ __noinline__ void hist_count_tuple(SearchCtl *ctl, int *ghist, int *ghmax, int hist_bins, const uint32_t *cnts, int nwc,
                                               bool valid, bool all) {
     int D[NCELLS];
 #pragma unroll
@@ -658,14 +705,16 @@ __device__ __noinline__ void hist_count_tuple(const SearchCtl *ctl, int *ghist, 
             const uint32_t w = cnts[k * NCELLS + c];
             t += max(U8 ? dp4a_us(w, sel, D[c]) : dp2a_lo_us(w, sel, D[c]), 0);
         }
-        bool on = valid && (all || t >= tq[f]);
+        const bool on = valid && (all || t >= tq[f]);
         const int m = __reduce_max_sync(0xffffffffu, on ? t : -1);
         if (m < 0) continue;
         if (all) {
-            // first unit: one pair per warp and fold, the best one -- the N best of the ~2400 warps' best pairs bound the
-            // N-th best of all their pairs almost as well, at 1/32 of the atomics on a handful of hot addresses
-            const unsigned best = __ballot_sync(0xffffffffu, on && t == m);
-            on = (threadIdx.x & 31) == (unsigned) (__ffs(best) - 1);
+            // first unit: the CTA keeps its best pair per fold in shared memory; the last warp through counts it into the
+            // global histogram (first_unit_done).  The N best of the CTAs' best pairs bound the N-th best of all their pairs
+            // well enough for the second units, at 148 atomics per hot address instead of one per warp -- which is what
+            // the second units' look-up has to wait for.
+            if ((threadIdx.x & 31) == 0) atomicMax(&ctl->first_best[f], m);
+            continue;
         }
         if (on) {
             atomicAdd(ghist + (size_t) f * hist_bins + t, 1);
@@ -673,6 +722,25 @@ __device__ __noinline__ void hist_count_tuple(const SearchCtl *ctl, int *ghist, 
             if (t == m) atomicMax(ghmax + f, m);     // fire and forget; several lanes at most when scores tie
         }
     }
+}
+
+// a warp is through with its share of the CTA's first unit (counted only): the last one publishes the CTA's best pairs
+__device__ __noinline__ void first_unit_done(SearchCtl *ctl, int *ghist, int *ghmax, int *gfirst, int hist_bins, int nwarps, int lane) {
+    __syncwarp();
+    if (lane != 0) return;
+    __threadfence_block();
+    if (atomicAdd(&ctl->first_done, 1) != nwarps - 1) return;
+    __threadfence_block();
+    const int F = ctl->fl.F;
+    for (int f = 0; f < F; f++) {
+        const int t = *reinterpret_cast<volatile int *>(&ctl->first_best[f]);
+        if (t < 0) continue;
+        atomicAdd(ghist + (size_t) f * hist_bins + t, 1);
+        atomicAdd(ghist + (size_t) F * hist_bins + (size_t) f * hist_coarse_bins(hist_bins) + (t >> 5), 1);
+        atomicMax(ghmax + f, t);
+    }
+    __threadfence();
+    atomicAdd(gfirst, 1);
 }
 
 // Fast version for balanced data sets (A == U <= 65535): every count pair travels as
@@ -683,13 +751,14 @@ __device__ __forceinline__ void epilogue_balanced_t(SearchCtl *ctl, const Search
                                                     int nthreads, bool valid, int si, int sj, int sk, int lane, int mode) {
     const int nfolds = ctl->fl.F;
     if constexpr (TRAINING) {
-        if (ctl->fl.eqfolds) {
+        if (a.prefilter) {
             if (mode == kModeCount) {                          // the CTA's first unit: counted now, offered at the end
                 hist_count_tuple<NCELLS, U8>(ctl, a.ghist, a.ghmax, a.hist_bins, cnts, nwc, valid, true);
                 return;
             }
             const bool pass = balanced_prefilter<NCELLS, U8>(ctl, cnts, nwc);
             if (!__any_sync(0xffffffffu, pass && valid)) return;
+            if ((threadIdx.x & 31) == 0) dbg_add(a, 0, 1);
             if (mode & kModeCount) hist_count_tuple<NCELLS, U8>(ctl, a.ghist, a.ghmax, a.hist_bins, cnts, nwc, valid, false);
         }
     }
@@ -860,7 +929,7 @@ __device__ __forceinline__ void refresh_threshold(SearchCtl *ctl, const SearchAr
     const long long g = __ldcg(a.gthr + f);
     if (g > *reinterpret_cast<volatile long long *>(&ctl->thr[f])) {
         atomicMax(&ctl->thr[f], g);
-        if (a.training) atomicMax(&ctl->tq[f], thr_quotient(g, ctl->fl.A - ctl->fl.a_in[f]));
+        if (a.prefilter) atomicMax(&ctl->tq[f], thr_quotient(g, ctl->fl.A - ctl->fl.a_in[f]));
     }
 }
 
@@ -877,7 +946,7 @@ __device__ __forceinline__ int warp_inclusive_scan(int v, int lane) {
     }
     return v;
 }
-__device__ __noinline__ void hist_threshold(SearchCtl *ctl, const int *ghist, const int *ghmax, int hist_bins, int rank, int f, int lane) {
+__device__ __noinline__ void hist_threshold(SearchCtl *ctl, const int *ghist, const int *ghmax, long long *gthr, int hist_bins, int rank, int f, int lane) {
     const int hmax = __ldcg(ghmax + f);
     const int cur = *reinterpret_cast<volatile int *>(&ctl->tq[f]);
     if (hmax < 0 || hmax < cur) return;
@@ -906,8 +975,10 @@ __device__ __noinline__ void hist_threshold(SearchCtl *ctl, const int *ghist, co
         cum += __shfl_sync(0xffffffffu, incl, 31);
     }
     if (lane == 0 && T != INT_MIN && T > cur) {
+        const long long sc = (long long) T * (ctl->fl.A - ctl->fl.a_in[f]);
         atomicMax(&ctl->tq[f], T);
-        atomicMax(&ctl->thr[f], (long long) T * (ctl->fl.A - ctl->fl.a_in[f]));
+        atomicMax(&ctl->thr[f], sc);
+        atomicMax(gthr + f, sc);                     // every other CTA adopts it at its next unit (refresh_threshold)
     }
 }
 
@@ -924,7 +995,8 @@ __device__ __forceinline__ void search_init(SearchCtl *ctl, const SearchArgs &a,
         ctl->fl = *a.fl;
     }
     if (tid < kMaxFolds) {
-        ctl->thr[tid] = LLONG_MIN; ctl->lock[tid] = 0; ctl->cnt[tid] = 0; ctl->root_seq[tid] = 0;
+        ctl->thr[tid] = LLONG_MIN; ctl->lock[tid] = 0; ctl->cnt[tid] = 0; ctl->root_seq[tid] = 0; ctl->first_best[tid] = -1;
+        if (tid == 0) ctl->first_done = 0;
         ctl->tq[tid] = tid < a.fl->F ? INT_MIN : INT_MAX;      // folds past F (odd F, byte-counter pairs) never pass
     }
     for (size_t x = tid; x < cnt_words; x += blockDim.x) cnt_base[x] = 0;   // halves that are never written must read 0
@@ -1031,6 +1103,7 @@ __global__ void __launch_bounds__((SINGLE ? kTriWarps : kMaxWarps) * 32, 1) sear
         }
     }
 
+    if (a.dbg && tid == 0) a.dbg[8 + 2 * blockIdx.x] = (unsigned long long) clock64();
     constexpr int NC = 9;
     uint32_t *cnts = cnt_base + (size_t) tid * counter_stride(NC, nwc);          // + k * NC + c
     uint32_t acc[9];
@@ -1057,14 +1130,29 @@ __global__ void __launch_bounds__((SINGLE ? kTriWarps : kMaxWarps) * 32, 1) sear
         const int ch = meta.x;
         if (s == 0 && a.stagger) stagger_late_warps(warp, TI, nblocks * 9 * (BW == 3 ? 18 : (BW == 4 ? 24 : 34)), a.stagger);
         if (ch == 0) {
+            // The best bound ANY CTA has derived (hist_threshold publishes its T, the lists publish their last entry): one L2
+            // read per fold and unit, by a different warp every unit so that no warp is always the one that pays the round
+            // trip.  Without it a CTA only learns about a strong SNP's pairs from its own share of them and from its own
+            // histogram look-ups (every 8th / 32nd unit), and its lists take in thousands of candidates that a fresher
+            // bound would have dropped (the slow rank of the 4- and 8-GPU runs of round 1).
+            if ((a.fresh_bound || !a.use_hist) && lane < ctl->fl.F && warp == (int) ((s / (uint32_t) nchunks) % (uint32_t) TI))
+                refresh_threshold(ctl, a, lane);
             if (a.use_hist) {
                 // every unit at first, then ever more rarely: the bound rises with the logarithm of the pairs seen, and
                 // the warps that pay the L2 round trips are late at the next hand-off of a stage
-                const uint32_t n = s / (uint32_t) nchunks;
-                if (n >= 1 && (n < 8 || (n < 64 ? (n & 7) == 0 : (n & 31) == 0)))
-                    for (int f = warp; f < ctl->fl.F; f += TI) hist_threshold(ctl, a.ghist, a.ghmax, a.hist_bins, a.rank, f, lane);
-            } else if (warp == 0 && lane < ctl->fl.F) {
-                refresh_threshold(ctl, a, lane);
+                // (staggered over the CTAs: somebody looks, and publishes, every unit)
+                const uint32_t n = s / (uint32_t) nchunks, m = n + blockIdx.x;
+                // The CTA's second unit is the first one whose pairs are offered, bounded by what ALL CTAs counted in their
+                // first units.  The CTAs run in lockstep, so without a wait this look-up races with the other CTAs' counting:
+                // when it finds fewer than N pairs the whole unit (640 pairs x F folds) is offered without a bound, and the
+                // lists take a six-figure number of insertions before the next look-up (the slow rank of round 1's 4- and
+                // 8-GPU runs).  All CTAs are co-resident (grid <= SMs, one CTA per SM); the wait is bounded all the same.
+                if (n == 1 && a.first_wait) {         // (every warp: the ones that do not look up must not run ahead to their epilogue)
+                    for (int spin = 0; spin < 20000 && *reinterpret_cast<volatile int *>(a.gfirst) < (int) gridDim.x; spin++) __nanosleep(100);
+                    __threadfence();
+                }
+                if (n >= 1 && (n < 8 || (n < 64 ? (m & 7) == 0 : (m & 31) == 0)))
+                    for (int f = warp; f < ctl->fl.F; f += TI) hist_threshold(ctl, a.ghist, a.ghmax, a.gthr, a.hist_bins, a.rank, f, lane);
             }
         }
 
@@ -1168,10 +1256,12 @@ __global__ void __launch_bounds__((SINGLE ? kTriWarps : kMaxWarps) * 32, 1) sear
                 if constexpr (BALANCED) epilogue_balanced<9, SINGLE>(ctl, a, lists, cnts, nwc, nthreads, valid, i, j, -1, lane, mode);
                 else epilogue_general<9, SINGLE>(ctl, a, lists, cnts, nwc, nthreads, valid, i, j, -1, lane);
             }
+            if (mode == kModeCount) first_unit_done(ctl, a.ghist, a.ghmax, a.gfirst, a.hist_bins, TI, lane);
         }
         if (++st == NS) { st = 0; ph ^= 1u; }
         if (++slot > NS) slot = 0;
     }
+    if (a.dbg && tid == 0) a.dbg[9 + 2 * blockIdx.x] = (unsigned long long) clock64();
     search_publish(ctl, a, lists);
 }
 
@@ -1360,20 +1450,6 @@ struct ModelOut {               // == hpgv_epi_model_t
     uint32_t conf[4];
 };
 
-struct Key128 {
-    unsigned long long hi, lo;
-};
-__device__ __forceinline__ bool key_ge(const Key128 &a, const Key128 &b) { return a.hi > b.hi || (a.hi == b.hi && a.lo >= b.lo); }
-__device__ __forceinline__ bool key_gt(const Key128 &a, const Key128 &b) { return a.hi > b.hi || (a.hi == b.hi && a.lo > b.lo); }
-__device__ __forceinline__ Key128 cand_key(const Cand &c, int order) {
-    Key128 k;
-    unsigned long long u = (unsigned long long) __double_as_longlong(c.ba);
-    k.hi = (u >> 63) ? ~u : (u | 0x8000000000000000ULL);             // larger BA -> larger key
-    unsigned long long t = order == 2 ? (((unsigned long long) (uint32_t) c.i << 32) | (uint32_t) c.j)
-                                      : (((unsigned long long) (uint32_t) c.i << 42) | ((unsigned long long) (uint32_t) c.j << 21) | (uint32_t) c.k);
-    k.lo = ~t;                                                        // smaller tuple -> larger key
-    return k;
-}
 __device__ __forceinline__ unsigned key_byte(const Key128 &k, int pass) {   // pass 0 = most significant byte
     return pass < 8 ? (unsigned) (k.hi >> (56 - 8 * pass)) & 0xffu : (unsigned) (k.lo >> (56 - 8 * (pass - 8))) & 0xffu;
 }
@@ -1436,7 +1512,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeArgs m)
             if (rank >= m.rank_out) continue;
             const Cand c = *entry(cidx[t]);
             ModelOut r;
-            r.accuracy = degenerate ? nan("") : c.ba;
+            r.accuracy = (degenerate || c.ba == -INFINITY) ? nan("") : c.ba;
             r.snp[0] = c.i; r.snp[1] = c.j; r.snp[2] = m.order == 3 ? c.k : -1;
             r.risky_mask = c.mask;
             r.conf[0] = (uint32_t) c.tp; r.conf[1] = (uint32_t) (npos - c.tp);
@@ -1503,7 +1579,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeArgs m)
         for (int o = 0; o < ns; o++) rank += key_gt(selkey[o], k) ? 1 : 0;
         const Cand c = *entry(selidx[t]);
         ModelOut r;
-        r.accuracy = degenerate ? nan("") : c.ba;
+        r.accuracy = (degenerate || c.ba == -INFINITY) ? nan("") : c.ba;
         r.snp[0] = c.i; r.snp[1] = c.j; r.snp[2] = m.order == 3 ? c.k : -1;
         r.risky_mask = c.mask;
         r.conf[0] = (uint32_t) c.tp; r.conf[1] = (uint32_t) (npos - c.tp);
@@ -1536,8 +1612,8 @@ __global__ void models_to_cands_kernel(const ModelOut *in, int64_t n, Cand *out)
 // Parity hook: explicit combinations, one warp each (simple on purpose)
 // ============================================================================
 __global__ void eval_kernel(const uint32_t *__restrict__ planes, const uint16_t *__restrict__ blk_desc,
-                            const FoldLayout *__restrict__ flp, int64_t snp_pad, int order, int training,
-                            int64_t ncomb, const int32_t *__restrict__ combs,
+                            const FoldLayout *__restrict__ flp, int64_t snp_pad, int order, int training, int eval_fn,
+                            int64_t ncomb, const int32_t *__restrict__ combs, const uint32_t *__restrict__ risky_in,
                             int32_t *counts_aff, int32_t *counts_unaff, uint32_t *risky_mask, uint32_t *conf, double *acc) {
     extern __shared__ int segcnt_all[];                 // [warps][nseg][C]
     const FoldLayout &fl = *flp;
@@ -1576,7 +1652,8 @@ __global__ void eval_kernel(const uint32_t *__restrict__ planes, const uint16_t 
             for (int g = 0; g < fl.F; g++) { totA += segcnt[(2 * g) * C + c]; totU += segcnt[(2 * g + 1) * C + c]; }
             const int inA = segcnt[(2 * f) * C + c], inU = segcnt[(2 * f + 1) * C + c];
             const int trA = totA - inA, trU = totU - inU;
-            const bool r = high_risk(trA, trU, rp);
+            // risky_in: the caller's own risky cells (confusion_matrix of model.c:337-460 takes them as an argument)
+            const bool r = risky_in ? ((risky_in[comb * fl.F + f] >> c) & 1u) != 0 : high_risk(trA, trU, rp);
             tp += r ? (training ? trA : inA) : 0;
             fp += r ? (training ? trU : inU) : 0;
             mask |= (r ? 1u : 0u) << c;
@@ -1590,8 +1667,22 @@ __global__ void eval_kernel(const uint32_t *__restrict__ planes, const uint16_t 
             uint32_t *m = conf + (comb * fl.F + f) * 4;
             m[0] = (uint32_t) tp; m[1] = (uint32_t) (npos - tp); m[2] = (uint32_t) fp; m[3] = (uint32_t) (nneg - fp);
         }
-        if (acc) acc[comb * fl.F + f] = (npos == 0 || nneg == 0) ? nan("") : balanced_accuracy(tp, fp, npos, nneg);
+        if (acc) acc[comb * fl.F + f] = evaluate_fn(eval_fn, tp, npos - tp, fp, nneg - fp);      // 0/0 = NaN like the reference
     }
+}
+
+// the device high-risk rule on explicit count pairs, and evaluate_model on explicit confusion matrices (parity hooks)
+__global__ void high_risk_kernel(const int32_t *__restrict__ ca, const int32_t *__restrict__ cu, int64_t n, int A, int U, int32_t *__restrict__ flags) {
+    const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    RiskParams rp;
+    rp.balanced = (A == U); rp.A = A; rp.U = U; rp.ratio = (float) A / (float) U;          // mdr.c:52
+    flags[t] = high_risk(ca[t], cu[t], rp) ? 1 : 0;
+}
+__global__ void evaluate_kernel(int eval_fn, int64_t n, const uint32_t *__restrict__ conf, double *__restrict__ out) {
+    const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    out[t] = evaluate_fn(eval_fn, (int) conf[4 * t], (int) conf[4 * t + 1], (int) conf[4 * t + 2], (int) conf[4 * t + 3]);
 }
 
 // ============================================================================

@@ -68,6 +68,15 @@ struct __attribute__((aligned(16))) Cand {
 };
 static_assert(sizeof(Cand) == 32, "Cand must be 32 bytes");
 
+// 128-bit ranking key: the canonical order (accuracy descending, then SNP tuple ascending) as "larger key first".
+struct __attribute__((aligned(16))) Key128 {
+    unsigned long long lo, hi;  // hi = order-preserving image of the accuracy, lo = ~tuple
+};
+
+// development trace (SearchArgs::dbg): offered tuples are appended after the counters and the per-CTA clocks
+constexpr unsigned long long kDbgTraceCount = 8 + 2 * 1024, kDbgTrace = kDbgTraceCount + 8, kDbgTraceCap = 1ULL << 20;
+constexpr unsigned long long kDbgWords = kDbgTrace + 2 * kDbgTraceCap;
+
 // Arguments of the order-2 / order-3 search kernels.
 struct SearchArgs {
     const uint32_t *planes;     // [nchunks][snp_pad][row_words]
@@ -92,12 +101,21 @@ struct SearchArgs {
     Cand *lists;                // [grid][F][rank]
     int *list_cnt;              // [grid][F]
     long long *gthr;            // [F] global score threshold (lower bound of the N-th best)
+    unsigned long long *dbg;    // development counters (HPGV_DEBUG_COUNTERS=1, read back with hpgv_epi_debug_counters), else nullptr:
+                                // [0] warps whose pre-filter passed, [1] lanes offered (score >= bound), [2] lanes left after the
+                                // root snapshot, [3] list entries written, [4] lock spins, [5] hist look-ups, [8 + 2b], [9 + 2b]: CTA b's
+                                // clock64 at its first step and at its end
+    int *gfirst;                // CTAs whose first unit is in the histogram
+    int first_wait;             // a CTA's second unit waits for gfirst == grid (HPGV_FIRST_WAIT=0: no wait, the look-up races)
+    int fresh_bound;            // adopt the best bound any CTA has published once per unit (HPGV_FRESH_BOUND=0: round-1 behaviour)
     // score histogram (balanced TRAINING searches with equal folds, order 2): ghist[f][t] counts the pairs seen so far
     // whose pre-filter score of fold f is t; the N-th best score any CTA can derive from it bounds every list
     int *ghist;                 // [F][hist_bins] fine bins, then [F][hist_coarse_bins(hist_bins)] bins of 32 scores
     int *ghmax;                 // [F] largest score counted so far (-1: none)
     int hist_bins;              // A + 1
     int use_hist;
+    int eval_fn;                // enum eval_function of model.h:84 (kEval* in epi_device.cuh); 1 = BA, the reference runner's choice (model.c:331)
+    int prefilter;              // balanced classes, equal folds, TRAINING part and BA: the pre-filter of epilogue_balanced_t applies
     int tri_derive;             // derive genotype 2 of SNP i from SNP j's marginals in blocks where i has no missing sample (rows with marg)
     int list_scan;              // short per-CTA lists (N <= 64) are plain arrays, one lock per warp and fold (offer_batch_scan); HPGV_LIST_SCAN
     int nstages;                // shared-memory stages of the search kernel's ring (2 or 3)

@@ -117,6 +117,35 @@ class EpistasisEngine:
         self._ck(self.lib.hpgv_epi_eval(self.h, order, eval_subset, n, _ptr(combs), _ptr(ca), _ptr(cu), _ptr(mask), _ptr(conf), _ptr(ba)))
         return dict(counts_aff=ca, counts_unaff=cu, risky_mask=mask, conf=conf, ba=ba)
 
+    def set_eval_function(self, eval_function):
+        """Which of evaluate_model's functions (model.c:462-479) ranks the models; default BA."""
+        self._ck(self.lib.hpgv_epi_set_eval_function(self.h, int(eval_function)))
+
+    def confusion(self, order, combs, risky_mask, eval_subset=SUBSET_TRAINING):
+        """confusion_matrix (model.c:337-460) for risky cells given by the caller: risky_mask [n, F]."""
+        combs = np.ascontiguousarray(combs, dtype=np.int32).reshape(-1, order)
+        n, F = combs.shape[0], self.num_folds
+        mask = np.ascontiguousarray(risky_mask, dtype=np.uint32).reshape(n, F)
+        conf = np.zeros((n, F, 4), np.uint32)
+        val = np.zeros((n, F), np.float64)
+        self._ck(self.lib.hpgv_epi_confusion(self.h, order, eval_subset, n, _ptr(combs), _ptr(mask), _ptr(conf), _ptr(val)))
+        return conf, val
+
+    def high_risk(self, counts_aff, counts_unaff, num_affected, num_unaffected):
+        """The device's high-risk rule (mdr.c:45-75) on explicit count pairs."""
+        ca = np.ascontiguousarray(counts_aff, dtype=np.int32).ravel()
+        cu = np.ascontiguousarray(counts_unaff, dtype=np.int32).ravel()
+        flags = np.zeros(ca.size, np.int32)
+        self._ck(self.lib.hpgv_epi_high_risk(self.h, _ptr(ca), _ptr(cu), ca.size, int(num_affected), int(num_unaffected), _ptr(flags)))
+        return flags.astype(bool)
+
+    def evaluate(self, conf, eval_function=1):
+        """evaluate_model (model.c:462-479) on the device: conf [n, 4] = {TP, FN, FP, TN}."""
+        m = np.ascontiguousarray(conf, dtype=np.uint32).reshape(-1, 4)
+        out = np.zeros(m.shape[0], np.float64)
+        self._ck(self.lib.hpgv_epi_evaluate(self.h, int(eval_function), m.shape[0], _ptr(m), _ptr(out)))
+        return out
+
     def unpack_masks(self, variant):
         _, a, u = self.dims()
         s_pad = 16 * ((a + 15) // 16) + 16 * ((u + 15) // 16)
@@ -136,6 +165,13 @@ class EpistasisEngine:
         if got < 0:
             self._ck(got)
         return [buf[i] for i in range(got)]
+
+    def debug_counters(self, n=8 + 2 * 148):
+        out = np.zeros(n, np.uint64)
+        got = self.lib.hpgv_epi_debug_counters(self.h, _ptr(out), n)
+        if got < 0:
+            self._ck(got)
+        return out[:got]
 
     def pipe_peak(self, kind, iters=2000):
         v = C.c_double()

@@ -39,6 +39,17 @@ extern "C" {
 #define HPGV_SUBSET_TESTING  0
 #define HPGV_SUBSET_TRAINING 1
 
+/* enum eval_function, model.h:84 { CA, BA, wBA, GAMMA, TAU_B } and evaluate_model, model.c:462-479.
+ * HPGV_EVAL_CA is what the reference EXECUTES for code 0: `if (!function) function = BA` (model.c:465-467) turns it
+ * into BA, which is also why test/test_epistasis_model.c:518-519 passes.  HPGV_EVAL_CA_TRUE is the documented formula
+ * (TP+TN)/(TP+FN+TN+FP) as an extension.  wBA is a TODO in the reference and is rejected (HPGV_E_UNSUPPORTED). */
+#define HPGV_EVAL_CA       0
+#define HPGV_EVAL_BA       1
+#define HPGV_EVAL_WBA      2
+#define HPGV_EVAL_GAMMA    3
+#define HPGV_EVAL_TAU_B    4
+#define HPGV_EVAL_CA_TRUE  5
+
 /* One ranked model = one (SNP combination, fold) evaluation.  Replaces
  * `risky_combination` (model.h:49-57): accuracy, combination[], and the risky
  * genotype tuples, here as a bit mask over the 3^order cells in the order
@@ -67,6 +78,11 @@ int hpgv_epi_set_stream(hpgv_epi_ctx *ctx, void *cuda_stream);
 
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t hpgv_epi_launch_count(const hpgv_epi_ctx *ctx);
+
+/* Evaluation function that ranks the models (and fills `accuracy`) in every later search / eval of this context.
+ * Default HPGV_EVAL_BA: the only one the reference's runner ever uses (model.c:331 hard-wires BA); the others are
+ * SURVEY 8(f)3.  A model whose value is NaN (0/0) ranks last, like in add_to_model_ranking (model.c:491). */
+int hpgv_epi_set_eval_function(hpgv_epi_ctx *ctx, int eval_function);
 
 /* ---- dataset: replaces epistasis_dataset_load/close (dataset.c:54-72) ---------
  * Genotypes are variant-major bytes, cases (affected) first then controls:
@@ -135,6 +151,19 @@ uint64_t hpgv_epi_num_combinations(int64_t num_variants, int order);
 int hpgv_epi_eval(hpgv_epi_ctx *ctx, int order, int eval_subset, int64_t num_combs, const int32_t *combs,
                   int32_t *counts_aff, int32_t *counts_unaff, uint32_t *risky_mask, uint32_t *conf, double *accuracy);
 
+/* confusion_matrix (model.c:337-460) for risky cells GIVEN by the caller (the reference passes them in a
+ * risky_combination): risky_mask_in is [num_combs][F], conf [num_combs][F][4], accuracy [num_combs][F]. */
+int hpgv_epi_confusion(hpgv_epi_ctx *ctx, int order, int eval_subset, int64_t num_combs, const int32_t *combs,
+                       const uint32_t *risky_mask_in, uint32_t *conf, double *accuracy);
+
+/* The device's high-risk rule (the function the search kernels call; mdr_high_risk_combinations2, mdr.c:45-75) on n
+ * explicit (affected, unaffected) count pairs with dataset sizes (num_affected, num_unaffected): flags[i] = 0/1. */
+int hpgv_epi_high_risk(hpgv_epi_ctx *ctx, const int32_t *counts_aff, const int32_t *counts_unaff, int64_t n,
+                       int num_affected, int num_unaffected, int32_t *flags);
+
+/* evaluate_model (model.c:462-479) on the device, the function the search kernels call: conf is [n][4] = {TP, FN, FP, TN}. */
+int hpgv_epi_evaluate(hpgv_epi_ctx *ctx, int eval_function, int64_t n, const uint32_t *conf, double *values);
+
 /* Unpack the GPU bit planes of one variant back to the reference's byte masks:
  * out is [3][S_pad] with 0xFF where genotype == g (set_genotypes_masks layout,
  * model.c:28-74; S_pad = 16*ceil(A/16) + 16*ceil(U/16)).  Parity hook for the packer. */
@@ -166,6 +195,11 @@ int hpgv_epi_last_search_ms(hpgv_epi_ctx *ctx, float *ms, int *grid);
  * launch: a caller that times a loop of steps enqueues them back to back and reads the durations once.
  * Returns the number of durations written (fewer than n when fewer launches were made). */
 int hpgv_epi_search_times(hpgv_epi_ctx *ctx, int n, float *ms);
+
+/* Development counters of the most recent search launched with HPGV_DEBUG_COUNTERS=1 in the environment (candidates that
+ * passed the pre-filter / reached a list / were stored, lock spins, per-CTA start and end clocks; epi_types.h SearchArgs::dbg).
+ * Returns the number of values written. */
+int hpgv_epi_debug_counters(hpgv_epi_ctx *ctx, uint64_t *out, int n);
 
 /* POPC / LOP3 pipe micro-benchmark (roofline denominator):
  * runs `iters` dependent-free rounds per thread on every SM and returns

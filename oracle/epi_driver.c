@@ -162,6 +162,19 @@ static int scratch_init(const drv_state *st, drv_scratch *sc) {
 }
 static void scratch_free(drv_scratch *sc) { free(sc->masks); free(sc->counts_aff); free(sc->counts_unaff); }
 
+/* Which of evaluate_model's functions (model.c:462-479) scores a model; BA is what the runner uses (model.c:331).
+ * Code 5 is the documented classification accuracy, which evaluate_model itself never reaches (code 0 becomes BA,
+ * model.c:465-467): written out here so that the product's extension has a checker. */
+static int g_eval_fn = BA;
+void DRV(set_eval_function)(int fn) { g_eval_fn = fn; }
+static double drv_evaluate(unsigned int *m) {
+    if (g_eval_fn == 5) {
+        double TP = m[0], FN = m[1], FP = m[2], TN = m[3];
+        return (TP + TN) / (TP + FN + TN + FP);
+    }
+    return evaluate_model(m, (enum eval_function) g_eval_fn);
+}
+
 /* One batch of n <= 16 combinations through the reference pipeline
  * (epistasis.c:4-93).  Outputs are indexed [comb][fold]. */
 static void eval_batch(const drv_state *st, drv_scratch *sc, int n, const int32_t *combs, int subset,
@@ -210,7 +223,7 @@ static void eval_batch(const drv_state *st, drv_scratch *sc, int n, const int32_
             begin += (int) num_risky[rc];
             if (risky_mask) risky_mask[o] = mask;
             if (conf) memcpy(conf + o * 4, m, sizeof(m));
-            if (ba) ba[o] = evaluate_model(m, BA);
+            if (ba) ba[o] = drv_evaluate(m);
         }
         free(risky_idx);
     }
@@ -472,5 +485,87 @@ int DRV(run_epistasis)(const char *dataset, const char *outdir, int order, int s
     opts.eval_subset = (enum evaluation_subset) eval_subset;
     opts.eval_mode = (enum evaluation_mode) eval_mode;
     return run_epistasis(&shared, &opts);
+}
+/* -------- reference only: merge_rankings (epistasis.c:96-153) and epistasis_report (epistasis_report.c:28-82) --------
+ * Per-fold rankings are given as model records (fold-major, `rank` slots per fold, snp[0] < 0 = empty slot).  They are
+ * turned into the reference's own `struct heap` of risky_combination exactly the way the runner fills them
+ * (risky_combination_new + add_to_model_ranking with the min comparator of the mode, singlenode/epistasis_runner.c:269-287),
+ * then handed to the reference's merge_rankings.  Used by tests/golden/make_golden.py to pin a16/a17. */
+static struct heap **heaps_from_models(int order, int F, int rank, const epi_model_rec *models, int eval_mode,
+                                       compare_risky_heap_func *min_out, compare_risky_heap_func *max_out) {
+    compare_risky_heap_func hmin = eval_mode == CV_A ? compare_risky_heap_accuracy_min : compare_risky_heap_count_min;
+    compare_risky_heap_func hmax = eval_mode == CV_A ? compare_risky_heap_accuracy_max : compare_risky_heap_count_max;
+    int ncells;
+    uint8_t **cells = get_genotype_combinations(order, &ncells);
+    masks_info info;
+    masks_info_init(order, ROW, 16, 16, &info);             /* only num_cell_counts_per_combination is read */
+    struct heap **h = malloc((size_t) F * sizeof(struct heap *));
+    for (int f = 0; f < F; f++) {
+        h[f] = malloc(sizeof(struct heap));
+        heap_init(h[f]);
+        for (int r = 0; r < rank; r++) {
+            const epi_model_rec *m = &models[(size_t) f * rank + r];
+            if (m->snp[0] < 0) continue;
+            int comb[3] = { m->snp[0], m->snp[1], m->snp[2] };
+            int idx[27], n = 0;
+            for (int c = 0; c < ncells; c++) if ((m->risky_mask >> c) & 1u) idx[n++] = c;
+            risky_combination *rc = risky_combination_new(order, comb, cells, n, idx, NULL, info);
+            rc->accuracy = m->ba;
+            if (add_to_model_ranking(rc, rank, h[f], hmin) < 0) risky_combination_free(rc);
+        }
+    }
+    for (int c = 0; c < ncells; c++) free(cells[c]);
+    free(cells);
+    *min_out = hmin; *max_out = hmax;
+    return h;
+}
+
+/* rows out (capacity cap): snp [cap][3], cv_count [cap], cv_accuracy [cap], num_risky [cap], genotypes [cap][27*3];
+ * returns the number of distinct combinations, in the order the reference's report would list them */
+int DRV(merge_rankings)(int order, int F, int rank, const epi_model_rec *models, int eval_mode, int cap,
+                        int32_t *snp, int32_t *cv_count, double *cv_accuracy, int32_t *num_risky, uint8_t *genotypes) {
+    compare_risky_heap_func hmin, hmax;
+    struct heap **h = heaps_from_models(order, F, rank, models, eval_mode, &hmin, &hmax);
+    struct heap *best = merge_rankings(F, h, hmin, hmax);
+    int n = 0;
+    while (!heap_empty(best)) {
+        struct heap_node *hn = heap_take(hmax, best);
+        risky_combination *e = (risky_combination *) hn->value;
+        if (n < cap) {
+            for (int s = 0; s < 3; s++) snp[n * 3 + s] = s < order ? e->combination[s] : -1;
+            cv_count[n] = e->cross_validation_count;
+            cv_accuracy[n] = e->accuracy;
+            num_risky[n] = e->num_risky_genotypes;
+            memcpy(genotypes + (size_t) n * 81, e->genotypes, (size_t) e->num_risky_genotypes * order);
+        }
+        n++;
+        risky_combination_free(e);
+        free(hn);
+    }
+    free(best);
+    for (int f = 0; f < F; f++) free(h[f]);
+    free(h);
+    return n;
+}
+
+int DRV(report)(int order, int F, int rank, const epi_model_rec *models, int eval_mode, int eval_subset, int cv_repetition,
+                int max_ranking_size, const char *path) {
+    compare_risky_heap_func hmin, hmax;
+    struct heap **h = heaps_from_models(order, F, rank, models, eval_mode, &hmin, &hmax);
+    struct heap *best = merge_rankings(F, h, hmin, hmax);
+    FILE *fd = fopen(path, "w");
+    if (!fd) return -1;
+    epistasis_report(order, cv_repetition, (enum evaluation_mode) eval_mode, (enum evaluation_subset) eval_subset, best,
+                     max_ranking_size, hmax, fd);
+    fclose(fd);
+    while (!heap_empty(best)) {
+        struct heap_node *hn = heap_take(hmax, best);
+        risky_combination_free((risky_combination *) hn->value);
+        free(hn);
+    }
+    free(best);
+    for (int f = 0; f < F; f++) free(h[f]);
+    free(h);
+    return 0;
 }
 #endif

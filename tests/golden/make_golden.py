@@ -14,6 +14,10 @@ Every case stores its inputs and the reference's outputs:
   kfolds   get_k_folds with the microsecond clock pinned (gettimeofday interposed)
   blocked  the reference's blocked enumeration (get_first/next_combination_in_block), defects and all
   formulas evaluate_model on the two matrices of test/test_epistasis_model.c:513-534
+  merge    the reference's own merge_rankings (epistasis.c:96-153) and epistasis_report (epistasis_report.c:28-82) on
+           per-fold rankings of an exhaustive search: rows in report order (CV-C, CV-A, kept risky cells) and the .epi
+           text, for CV-A and CV-C.  Inputs are chosen tie-free (distinct CV-A values; CV-A monotone in CV-C so that the
+           reference's CV-C comparator, model.c:525-543, is a consistent order -- SURVEY F9), the generator asserts it.
 """
 import base64
 import itertools
@@ -32,6 +36,42 @@ from hpg_variant_b200 import synth  # noqa: E402
 
 def b64(a):
     return base64.b64encode(np.ascontiguousarray(a).tobytes()).decode()
+
+
+def tie_free(rows):
+    accs = [r[2] for r in rows]
+    if len(set(accs)) != len(accs) or any(np.isnan(a) for a in accs):
+        return False
+    # a higher CV-C never comes with a lower CV-A: compare_risky_heap_count_max is then a consistent strict order
+    return all(not (a[1] > b[1] and a[2] < b[2]) for a in rows for b in rows)
+
+
+def merge_cases(ref):
+    import tempfile
+    cases = []
+    for order, nv, A, U, F, rank, subset in [(2, 14, 90, 110, 5, 6, 1), (2, 12, 700, 640, 4, 8, 0), (3, 8, 80, 70, 3, 7, 1), (2, 10, 149, 198, 10, 3, 1)]:
+        for seed in range(1000):
+            g = synth.make_dataset(nv, A, U, seed=9000 + seed, order=order, missing=0.01, planted=2)
+            rng = np.random.default_rng(seed)
+            fos = np.concatenate([rng.permutation(A) % F, rng.permutation(U) % F]).astype(np.int32)
+            top, _ = ref.search(g, A, U, order, fos, subset, rank, threads=2, num_folds=F)
+            models = np.zeros((F, rank), oracle_lib.MODEL_DTYPE)
+            models[:] = top
+            rows_a = ref.merge_rankings(order, models, 1)
+            rows_c = ref.merge_rankings(order, models, 0)
+            if tie_free(rows_a) and tie_free(rows_c) and any(r[1] > 1 for r in rows_a) and any(r[1] < F for r in rows_a):
+                break
+        else:
+            raise SystemExit(f"no tie-free merge case found for {(order, nv, A, U, F, rank, subset)}")
+        rec = {"order": order, "nv": nv, "A": A, "U": U, "F": F, "rank": rank, "subset": subset, "dataset_seed": 9000 + seed,
+               "genotypes": b64(g), "fold_of_sample": b64(fos), "models": b64(models), "modes": {}}
+        for mode, rows in ((0, rows_c), (1, rows_a)):
+            with tempfile.TemporaryDirectory() as tmp:
+                text = ref.report(order, models, mode, subset, 2, rank + 3, os.path.join(tmp, "r.epi"))
+            rec["modes"][str(mode)] = {"rows": [[list(r[0]), r[1], r[2].hex(), r[3]] for r in rows], "report": text,
+                                       "cv_repetition": 2, "max_ranking_size": rank + 3}
+        cases.append(rec)
+    return cases
 
 
 def main():
@@ -92,6 +132,8 @@ def main():
 
     for m in ([40, 2, 4, 10], [20, 10, 10, 20]):
         out["formulas"].append({"conf": m, "values": [ref.evaluate(m, fn) for fn in (0, 1, 3, 4)], "functions": ["CA", "BA", "GAMMA", "TAU_B"]})
+
+    out["merge"] = merge_cases(ref)
 
     path = os.path.join(HERE, "epi_golden.json")
     with open(path, "w") as fh:

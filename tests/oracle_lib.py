@@ -109,6 +109,10 @@ class Checker:
             raise RuntimeError(f"{self.pfx}search failed: {rc}")
         return out, n_out
 
+    def set_eval_function(self, fn):
+        """evaluate_model's function code for eval()/search() (1 = BA, the default; 5 = documented CA)."""
+        self._fn("set_eval_function")(C.c_int(fn))
+
     # ---- leaf helpers -----------------------------------------------------------
     def k_folds(self, A, U, k, seed):
         fos = np.full(A + U, -1, np.int32)
@@ -145,6 +149,42 @@ class Checker:
         comb = np.zeros(order, np.int32)
         self._fn("unrank")(C.c_int(nv), C.c_int(order), C.c_uint64(idx), _p(comb, C.c_int32))
         return comb
+
+    # ---- reference only: merge_rankings + epistasis_report on given per-fold rankings ------------
+    def merge_rankings(self, order, models, mode):
+        """models: structured [F, rank] (MODEL_DTYPE, empty slots snp[0] < 0); mode 0 = CV_C, 1 = CV_A.
+        Returns the rows in the order the reference's report lists them: (snp tuple, cv_count, cv_accuracy, risky cells)."""
+        assert self.kind == "ref"
+        m = np.ascontiguousarray(models)
+        F, rank = m.shape
+        cap = F * rank
+        snp = np.zeros((cap, 3), np.int32)
+        cnt = np.zeros(cap, np.int32)
+        acc = np.zeros(cap, np.float64)
+        nr = np.zeros(cap, np.int32)
+        gts = np.zeros((cap, 81), np.uint8)
+        f = self._fn("merge_rankings")
+        f.restype = C.c_int
+        n = f(C.c_int(order), C.c_int(F), C.c_int(rank), m.ctypes.data_as(C.c_void_p), C.c_int(mode), C.c_int(cap),
+              _p(snp, C.c_int32), _p(cnt, C.c_int32), _p(acc, C.c_double), _p(nr, C.c_int32), _p(gts, C.c_uint8))
+        rows = []
+        for r in range(n):
+            cells = [int(sum(int(gts[r, q * order + p]) * 3 ** (order - 1 - p) for p in range(order))) for q in range(nr[r])]
+            rows.append((tuple(int(x) for x in snp[r, :order]), int(cnt[r]), float(acc[r]), cells))
+        return rows
+
+    def report(self, order, models, mode, subset, cv_repetition, max_ranking_size, path):
+        assert self.kind == "ref"
+        m = np.ascontiguousarray(models)
+        F, rank = m.shape
+        f = self._fn("report")
+        f.restype = C.c_int
+        rc = f(C.c_int(order), C.c_int(F), C.c_int(rank), m.ctypes.data_as(C.c_void_p), C.c_int(mode), C.c_int(subset),
+               C.c_int(cv_repetition), C.c_int(max_ranking_size), str(path).encode())
+        if rc != 0:
+            raise RuntimeError("ref_report failed")
+        with open(path) as fh:
+            return fh.read()
 
     # ---- reference only: its own end-to-end runner ------------------------------
     def run_epistasis(self, dataset, outdir, order, stride, num_folds, reps, rank_size, subset, mode, threads):

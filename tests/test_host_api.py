@@ -37,8 +37,7 @@ class ReportRow(C.Structure):
                 ("num_risky", C.c_int), ("risky_genotypes", (C.c_uint8 * 3) * 27)]
 
 
-@pytest.fixture(scope="module")
-def host():
+def load_host():
     if not os.path.exists(HOSTLIB):
         hbuild.build()
     lib = C.CDLL(HOSTLIB)
@@ -55,6 +54,11 @@ def host():
     lib.hpgv_epi_merge_rankings.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(ReportRow), C.c_int]
     lib.epistasis.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_char_p]
     return lib
+
+
+@pytest.fixture(scope="module")
+def host():
+    return load_host()
 
 
 def test_host_library_exports_the_reference_api(host):
@@ -251,6 +255,48 @@ def test_merge_rankings_and_report(host, tmp_path, order, mode):
     host.hpgv_epi_write_report(order, 2, 0 if mode == "count" else 1, 1, rows, n, 10, fd)
     libc.fclose(fd)
     assert path.read_text() == py_report(want, order, 2, mode, "training", 10)
+
+
+def _write_report(host, tmp_path, order, rep, mode, subset, rows, n, max_rank):
+    path = tmp_path / f"r{mode}.epi"
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    fd = libc.fopen(str(path).encode(), b"w")
+    host.hpgv_epi_write_report.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(ReportRow), C.c_int, C.c_int, C.c_void_p]
+    host.hpgv_epi_write_report(order, rep, mode, subset, rows, n, max_rank, fd)
+    libc.fclose(fd)
+    return path.read_text()
+
+
+def check_against_reference_merge(host, tmp_path, case, models):
+    """models [F, rank] (h.MODEL_DTYPE) -> hpgv_epi_merge_rankings / hpgv_epi_write_report == what the reference's own
+    merge_rankings + epistasis_report made of the same per-fold rankings (tests/golden, `merge`)."""
+    from golden_util import unb64
+    order, F, rank = case["order"], case["F"], case["rank"]
+    for mode in (0, 1):
+        gold = case["modes"][str(mode)]
+        rows = (ReportRow * (F * rank))()
+        n = host.hpgv_epi_merge_rankings(order, F, rank, models.ctypes.data, mode, rows, F * rank)
+        assert n == len(gold["rows"])
+        for r, (snp, cvc, cva_hex, cells) in zip(rows, gold["rows"]):
+            assert list(r.snp[:order]) == snp and r.cv_count == cvc
+            assert r.cv_accuracy == float.fromhex(cva_hex)              # same additions in the same order, then / F
+            got_cells = [sum(int(r.risky_genotypes[q][p]) * 3 ** (order - 1 - p) for p in range(order)) for q in range(r.num_risky)]
+            assert got_cells == cells                                   # the risky genotypes of the fold the reference keeps
+        text = _write_report(host, tmp_path, order, gold["cv_repetition"], mode, case["subset"], rows, n, gold["max_ranking_size"])
+        assert text == gold["report"]
+
+
+@pytest.mark.parametrize("idx", range(len(GOLD["merge"])))
+def test_merge_rankings_and_report_match_the_reference(host, tmp_path, idx):
+    """a16/a17: rows and .epi bytes against goldens produced by the reference's merge_rankings (epistasis.c:96-153) and
+    epistasis_report (epistasis_report.c:28-82) -- tests/golden/make_golden.py, tie-free inputs."""
+    from golden_util import unb64
+    case = GOLD["merge"][idx]
+    models = unb64(case["models"], h.MODEL_DTYPE, (case["F"], case["rank"]))
+    check_against_reference_merge(host, tmp_path, case, models)
 
 
 def test_report_line_format_of_the_reference():
