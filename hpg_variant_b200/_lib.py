@@ -40,7 +40,7 @@ SYMBOLS = [
     "hpgv_epi_num_combinations", "hpgv_epi_eval", "hpgv_epi_unpack_masks", "hpgv_epi_run_host", "hpgv_epi_layout",
     "hpgv_epi_pipe_peak", "hpgv_epi_last_search_ms", "hpgv_epi_search_times",
     "hpgv_epi_set_eval_function", "hpgv_epi_confusion", "hpgv_epi_high_risk", "hpgv_epi_evaluate",
-    "hpgv_epi_debug_counters",
+    "hpgv_epi_debug_counters", "hpgv_epi_merge_host", "hpgv_epi_device_count",
 ]
 
 
@@ -85,5 +85,7 @@ def load():
     lib.hpgv_epi_high_risk.argtypes = [vp, vp, vp, i64, i32, i32, vp]
     lib.hpgv_epi_evaluate.argtypes = [vp, i32, i64, vp, vp]
     lib.hpgv_epi_debug_counters.argtypes = [vp, vp, i32]
+    lib.hpgv_epi_merge_host.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
+    lib.hpgv_epi_device_count.argtypes = []
     _lib = lib
     return lib

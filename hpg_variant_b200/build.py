@@ -47,11 +47,12 @@ def build(force=False, verbose=False):
     if os.path.exists(host_src):
         compat = os.path.join(os.path.dirname(HERE), "include", "hpgv_epi_compat.h")
         if force or _newer(HOSTLIB, [host_src, compat] + inc + [LIB]):
-            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I/usr/local/cuda/include", "-o", HOSTLIB, host_src,
-                            "-L" + HERE, "-lhpgv_epi", "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath,$ORIGIN"], check=True, env=_env())
+            # no CUDA runtime here: everything that touches the GPU goes through the C-ABI of libhpgv_epi.so
+            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", HOSTLIB, host_src,
+                            "-L" + HERE, "-lhpgv_epi", "-Wl,-rpath,$ORIGIN"], check=True, env=_env())
         cli_src = os.path.join(CSRC, "epi_cli.cpp")
         if os.path.exists(cli_src) and (force or _newer(CLI, [cli_src, HOSTLIB])):
-            subprocess.run(["g++", "-O2", "-std=c++17", "-o", CLI, cli_src, "-L" + HERE, "-lhpgv_epi_host", "-lhpgv_epi",
+            subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-o", CLI, cli_src, "-L" + HERE, "-lhpgv_epi_host", "-lhpgv_epi",
                             "-Wl,-rpath,$ORIGIN"], check=True, env=_env())
     return LIB
 

@@ -84,6 +84,11 @@ struct hpgv_epi_ctx {
     DevBuf<int32_t> d_jt0;
     DevBuf<int2> d_unit_desc;
     bool wl_has_desc = false;
+    // search3v2_kernel: per-SNP lists of missing samples (made on the first order-3 search after set_folds)
+    DevBuf<uint32_t> d_miss;
+    DevBuf<int> d_miss_max;
+    bool miss_valid = false;
+    int miss_cap = 0;
     DevBuf<hpgv_epi_model_t> d_out;
     DevBuf<Cand> d_merge_in;
     // cached work list
@@ -176,7 +181,7 @@ extern "C" void hpgv_epi_destroy(hpgv_epi_ctx *ctx) {
     cudaSetDevice(ctx->device);
     ctx->raw_owned.release(); ctx->d_fl.release(); ctx->d_perm.release(); ctx->d_blk.release(); ctx->d_planes.release();
     ctx->d_lists.release(); ctx->d_list_cnt.release(); ctx->d_gthr.release(); ctx->d_hist.release(); ctx->d_hmax.release(); ctx->d_dbg.release();
-    ctx->d_prefix.release(); ctx->d_jt0.release(); ctx->d_unit_desc.release(); ctx->d_out.release(); ctx->d_merge_in.release();
+    ctx->d_prefix.release(); ctx->d_jt0.release(); ctx->d_unit_desc.release(); ctx->d_out.release(); ctx->d_merge_in.release(); ctx->d_miss.release(); ctx->d_miss_max.release();
     for (int k = 0; k < hpgv_epi_ctx::kEvRing; k++) { if (ctx->ev0[k]) cudaEventDestroy(ctx->ev0[k]); if (ctx->ev1[k]) cudaEventDestroy(ctx->ev1[k]); }
     if (ctx->ev_stage) cudaEventDestroy(ctx->ev_stage);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -388,6 +393,7 @@ static int apply_folds(hpgv_epi_ctx *ctx, int F, const int32_t *fold_of_sample, 
         }
     }
     ctx->fl = fl;
+    ctx->miss_valid = false;
     // rows are padded so that every tile a kernel stages (<= 32 rows past any valid origin) stays inside the buffer
     ctx->snp_pad = ((ctx->nv + kTileJ - 1) / kTileJ) * kTileJ + kTileJ;
     ctx->plane_words = (size_t) fl.nchunks * (size_t) ctx->snp_pad * fl.row_words;
@@ -687,6 +693,87 @@ static int launch_merge(hpgv_epi_ctx *ctx, const MergeArgs &m) {
     return HPGV_OK;
 }
 
+// ---- order 3, resident (j, k) tiles (search3v2_kernel) ---------------------------------------------------------------
+struct Shape3 {
+    int tj = 0, ni = 0;
+    bool lists_in_smem = false;
+    size_t smem = 0;
+};
+static Shape3 pick_shape3(const hpgv_epi_ctx *ctx, int rank, int mcap) {
+    const FoldLayout &fl = ctx->fl;
+    Shape3 best;
+    if (fl.tri || fl.nchunks > 15 || fl.cb * 3 * fl.bw > 2047 || fl.nblocks / 4 > 1023) return best;
+    for (int tj = 8; tj >= 4; tj -= 2)
+        for (int in_smem = 1; in_smem >= 0; in_smem--) {
+            if (in_smem && (size_t) fl.F * rank * sizeof(Cand) > 24 * 1024) continue;
+            for (int ni = 4; ni >= 1; ni >>= 1) {
+                const Smem3Map m = search3v2_smem_map(fl, tj, ni, 2, mcap, rank, in_smem != 0);
+                if (m.total <= (size_t) ctx->max_smem_optin) {
+                    best.tj = tj; best.ni = ni; best.lists_in_smem = in_smem != 0; best.smem = m.total;
+                    return best;
+                }
+            }
+        }
+    return best;
+}
+
+// lists of missing samples per SNP; returns the list capacity (entries per SNP incl. the end marker), 0 when some SNP misses too much
+static int build_miss_lists(hpgv_epi_ctx *ctx) {
+    if (ctx->miss_valid) return ctx->miss_cap;
+    const int64_t rows = ctx->snp_pad;
+    const int threads = 256;
+    const unsigned grid = (unsigned) ((rows * 32 + threads - 1) / threads);
+    CK(ctx->d_miss_max.reserve(1));
+    CK(cudaMemsetAsync(ctx->d_miss_max.p, 0, sizeof(int), ctx->stream));
+    miss_list_kernel<<<grid, threads, 0, ctx->stream>>>(ctx->d_raw, ctx->nv, rows, ctx->A + ctx->U, ctx->d_perm.p, ctx->d_fl.p, ctx->d_blk.p, ctx->npos,
+                                                        0, nullptr, ctx->d_miss_max.p);
+    CK(cudaGetLastError());
+    int mx = 0;
+    CK(cudaMemcpyAsync(&mx, ctx->d_miss_max.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->launches++;
+    ctx->miss_valid = true;
+    ctx->miss_cap = 0;
+    if (mx > 250) return 0;                           // that many missing samples per SNP: the plain kernel counts every cell instead
+    const int mcap = (mx + 1 + 3) / 4 * 4;            // + end marker, 16-byte multiples (bulk copies)
+    CK(ctx->d_miss.reserve((size_t) rows * mcap));
+    miss_list_kernel<<<grid, threads, 0, ctx->stream>>>(ctx->d_raw, ctx->nv, rows, ctx->A + ctx->U, ctx->d_perm.p, ctx->d_fl.p, ctx->d_blk.p, ctx->npos,
+                                                        mcap, ctx->d_miss.p, ctx->d_miss_max.p);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    ctx->miss_cap = mcap;
+    return mcap;
+}
+
+// units of search3v2_kernel: (j tile, k tile) pairs that hold some j < k, longest i loops first
+static int build_worklist3(hpgv_epi_ctx *ctx, int tj, uint64_t first, uint64_t last) {
+    if (ctx->wl_nv == ctx->nv && ctx->wl_order == 3 && ctx->wl_ti == -tj && ctx->wl_first == first && ctx->wl_last == last) return HPGV_OK;
+    const int64_t nv = ctx->nv;
+    std::vector<int2> desc;
+    int64_t i_first = 0, i_last = -1;
+    if (first < last) {
+        i_first = unrank_triple_first((uint64_t) nv, first);
+        i_last = unrank_triple_first((uint64_t) nv, last - 1);
+        const int64_t njt = (nv - 1 + tj - 1) / tj, nkt = (nv + kTileJ - 1) / kTileJ;
+        for (int64_t jt = njt - 1; jt >= 0; jt--) {
+            const int64_t j0 = jt * tj;
+            if (j0 + tj - 1 <= i_first) break;        // no j of this tile (or of any before it) lies past the range's first i
+            for (int64_t kt = (j0 + 1) / kTileJ; kt < nkt; kt++) desc.push_back(make_int2((int) j0, (int) (kt * kTileJ)));
+            if ((int64_t) desc.size() > ((int64_t) 4 << 20)) FAIL(HPGV_E_UNSUPPORTED, "order-3 unit list too long");
+        }
+    }
+    if (!desc.empty()) {
+        CK(ctx->d_unit_desc.reserve(desc.size()));
+        CK(cudaMemcpyAsync(ctx->d_unit_desc.p, desc.data(), desc.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->wl_nv = nv; ctx->wl_order = 3; ctx->wl_ti = -tj; ctx->wl_first = first; ctx->wl_last = last;
+    ctx->wl_units = (int64_t) desc.size();
+    ctx->wl_edge_lo = (int) i_first; ctx->wl_edge_hi = (int) i_last;
+    ctx->wl_has_desc = true;
+    return HPGV_OK;
+}
+
 static int do_search(hpgv_epi_ctx *ctx, int order, int eval_subset, int rank, uint64_t first, uint64_t last,
                      hpgv_epi_model_t *d_out) {
     if (!ctx->folds_set) FAIL(HPGV_E_STATE, "search before set_folds");
@@ -731,10 +818,29 @@ static int do_search(hpgv_epi_ctx *ctx, int order, int eval_subset, int rank, ui
         args.tri_derive = !(td && td[0] == '0');
     }
 
-    const SearchShape shape = pick_shape(ctx, order, rank);
+    // order 3: the kernel with resident (j, k) tiles when its tables fit shared memory and no SNP misses hundreds of samples
+    bool use_v2 = false;
+    SearchShape shape;
+    if (order == 3) {
+        const char *v2 = getenv("HPGV_SEARCH3_V2");           // A/B switch: "0" keeps the plain order-3 kernel
+        if (!(v2 && v2[0] == '0')) {
+            const int mcap = build_miss_lists(ctx);
+            if (mcap < 0) return mcap;
+            const Shape3 s3 = mcap > 0 ? pick_shape3(ctx, rank, mcap) : Shape3();
+            if (s3.tj > 0) {
+                int rc3 = build_worklist3(ctx, s3.tj, first, last);
+                if (rc3 == HPGV_OK) {
+                    use_v2 = true;
+                    shape.nthreads = 2 * s3.tj * 32; shape.lists_in_smem = s3.lists_in_smem; shape.nstages = 2; shape.smem = s3.smem;
+                    args.v2_ni = s3.ni; args.v2_mcap = mcap; args.v2_miss = ctx->d_miss.p;
+                } else if (rc3 != HPGV_E_UNSUPPORTED) return rc3;
+            }
+        }
+    }
+    if (!use_v2) shape = pick_shape(ctx, order, rank);
     if (shape.nthreads == 0)
         FAIL(HPGV_E_UNSUPPORTED, "fold count x cell count does not fit the shared memory of an SM (" + std::to_string(ctx->max_smem_optin) + " bytes)");
-    int rc = build_worklist(ctx, order, shape.nthreads / 32, first, last);
+    int rc = use_v2 ? HPGV_OK : build_worklist(ctx, order, shape.nthreads / 32, first, last);
     if (rc) return rc;
     args.unit_prefix = ctx->d_prefix.p;
     args.unit_jt0 = ctx->d_jt0.p;
@@ -776,6 +882,7 @@ static int do_search(hpgv_epi_ctx *ctx, int order, int eval_subset, int rank, ui
     if (order == 2 && fl.tri) grid = balanced ? launch_search(ctx, search2_kernel<3, true, true>, shape, args, F, rank)
                                               : launch_search(ctx, search2_kernel<3, true, false>, shape, args, F, rank);
     else if (order == 2) HPGV_LAUNCH(search2_kernel);
+    else if (use_v2) HPGV_LAUNCH(search3v2_kernel);
     else HPGV_LAUNCH(search3_kernel);
 #undef HPGV_LAUNCH
     if (grid < 0) return grid;
@@ -827,6 +934,32 @@ extern "C" int hpgv_epi_merge_device(hpgv_epi_ctx *ctx, int order, int eval_subs
     m.training = (eval_subset == HPGV_SUBSET_TRAINING);
     m.fl = ctx->d_fl.p; m.out = d_out; m.order = order;
     return launch_merge(ctx, m);
+}
+
+extern "C" int hpgv_epi_merge_host(hpgv_epi_ctx *ctx, int order, int eval_subset, int num_lists, int F, int rank,
+                                   const hpgv_epi_model_t *lists, hpgv_epi_model_t *out) {
+    if (!ctx || !lists || !out) return HPGV_E_ARG;
+    if (num_lists < 1 || F < 1 || rank < 1 || rank > kMaxRank) FAIL(HPGV_E_ARG, "bad list shape");
+    CK(cudaSetDevice(ctx->device));
+    const size_t nin = (size_t) num_lists * F * rank, nout = (size_t) F * rank;
+    hpgv_epi_model_t *d = nullptr;
+    CK(cudaMalloc(&d, (nin + nout) * sizeof(hpgv_epi_model_t)));
+    cudaError_t e = cudaMemcpyAsync(d, lists, nin * sizeof(hpgv_epi_model_t), cudaMemcpyHostToDevice, ctx->stream);
+    int rc = HPGV_OK;
+    if (e == cudaSuccess) rc = hpgv_epi_merge_device(ctx, order, eval_subset, num_lists, F, rank, d, d + nin);
+    if (e == cudaSuccess && rc == HPGV_OK) e = cudaMemcpyAsync(out, d + nin, nout * sizeof(hpgv_epi_model_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (rc) return rc;
+    if (e != cudaSuccess) FAIL(HPGV_E_CUDA, std::string("merge_host: ") + cudaGetErrorString(e));
+    return HPGV_OK;
+}
+
+extern "C" int hpgv_epi_device_count(void) {
+    int n = 0;
+    const cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { g_create_error = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e); return 0; }
+    return n;
 }
 
 // ---------------------------------------------------------------------------------

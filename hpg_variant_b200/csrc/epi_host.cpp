@@ -6,7 +6,6 @@
 #include "../../include/hpgv_epi_compat.h"
 #include "../../include/hpgv_epi.h"
 
-#include <cuda_runtime_api.h>
 #include <errno.h>
 #include <fcntl.h>
 #include <stdarg.h>
@@ -22,6 +21,7 @@
 #include <cmath>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 // -------------------------------------------------------------------------------------
@@ -317,14 +317,17 @@ extern "C" int run_epistasis(shared_options_data_t *shared, epistasis_options_da
     else LOGF("Rank criteria not specified! Must be 'count' or 'accu'\n");
     if (order != 2 && order != 3) LOGF("Combinations of order %d are not supported by the GPU engine (2 or 3)\n", order);
 
-    // one engine context per GPU; the combination index space is cut into contiguous ranges
+    // one engine context per GPU; the combination index space is cut into contiguous ranges.  Everything that touches
+    // CUDA goes through the C-ABI of libhpgv_epi.so: this library links no CUDA runtime of its own.
     int ngpu = (int) env_long("HPGV_EPI_GPUS", 1);
-    int have = 0;
-    if (cudaGetDeviceCount(&have) != cudaSuccess || have < 1) LOGF("No CUDA device is available: the epistasis engine has no CPU path\n");
+    const int have = hpgv_epi_device_count();
+    if (have < 1) LOGF("No CUDA device is available: the epistasis engine has no CPU path (%s)\n", hpgv_epi_last_error(nullptr));
     ngpu = std::max(1, std::min(ngpu, have));
     std::vector<hpgv_epi_ctx *> ctx((size_t) ngpu, nullptr);
+    const int eval_fn = (int) env_long("HPGV_EPI_EVAL_FUNCTION", HPGV_EVAL_BA);
     for (int g = 0; g < ngpu; g++) {
         if (hpgv_epi_create(g, &ctx[g]) != HPGV_OK) LOGF("GPU %d: %s\n", g, hpgv_epi_last_error(nullptr));
+        if (hpgv_epi_set_eval_function(ctx[g], eval_fn) != HPGV_OK) LOGF("GPU %d: %s\n", g, hpgv_epi_last_error(ctx[g]));
         if (hpgv_epi_load_dataset_host(ctx[g], genotypes, (int64_t) num_variants, num_affected, num_unaffected) != HPGV_OK)
             LOGF("GPU %d: %s\n", g, hpgv_epi_last_error(ctx[g]));
     }
@@ -341,40 +344,32 @@ extern "C" int run_epistasis(shared_options_data_t *shared, epistasis_options_da
         LOGI("Running cross-validation #%d...\n", r + 1);
         if (hpgv_epi_k_folds(num_affected, num_unaffected, num_folds, seeded ? seed0 + r : clock_seed(), fos.data(), nullptr) != HPGV_OK)
             LOGF("Cannot draw %d folds\n", num_folds);
-        for (int g = 0; g < ngpu; g++)
-            if (hpgv_epi_set_folds(ctx[g], num_folds, fos.data()) != HPGV_OK) LOGF("GPU %d: %s\n", g, hpgv_epi_last_error(ctx[g]));
         if (ngpu == 1) {
+            if (hpgv_epi_set_folds(ctx[0], num_folds, fos.data()) != HPGV_OK) LOGF("GPU 0: %s\n", hpgv_epi_last_error(ctx[0]));
             if (hpgv_epi_search(ctx[0], order, opt->eval_subset, rank, 0, total, models.data()) != HPGV_OK)
                 LOGF("GPU 0: %s\n", hpgv_epi_last_error(ctx[0]));
         } else {
-            // every GPU searches its range (the launches are asynchronous), then GPU 0 merges the per-range rankings
-            std::vector<hpgv_epi_model_t *> d_part((size_t) ngpu, nullptr);
+            // One host thread per GPU (the role of the MPI ranks of mpi/epistasis_runner.c:129-157): pack, search the GPU's
+            // range, bring its F x N models back.  hpgv_epi_search synchronises its own stream before it returns, so
+            // nothing here depends on how streams of different contexts order.  GPU 0 then merges (mpi/...:410-452).
+            std::vector<int> rcs((size_t) ngpu, HPGV_OK);
+            std::vector<std::thread> workers;
             for (int g = 0; g < ngpu; g++) {
-                cudaSetDevice(g);
-                if (cudaMalloc((void **) &d_part[g], nrec * sizeof(hpgv_epi_model_t)) != cudaSuccess) LOGF("GPU %d: out of memory\n", g);
-                const uint64_t lo = total / ngpu * g + std::min<uint64_t>(g, total % ngpu);
-                const uint64_t hi = total / ngpu * (g + 1) + std::min<uint64_t>(g + 1, total % ngpu);
-                if (hpgv_epi_search_device(ctx[g], order, opt->eval_subset, rank, lo, hi, d_part[g]) != HPGV_OK)
-                    LOGF("GPU %d: %s\n", g, hpgv_epi_last_error(ctx[g]));
+                workers.emplace_back([&, g]() {
+                    const uint64_t lo = total / ngpu * g + std::min<uint64_t>(g, total % ngpu);
+                    const uint64_t hi = total / ngpu * (g + 1) + std::min<uint64_t>(g + 1, total % ngpu);
+                    int rc = hpgv_epi_set_folds(ctx[g], num_folds, fos.data());
+                    if (rc == HPGV_OK) rc = hpgv_epi_search(ctx[g], order, opt->eval_subset, rank, lo, hi, part.data() + nrec * g);
+                    rcs[g] = rc;
+                });
             }
+            for (auto &w : workers) w.join();
             for (int g = 0; g < ngpu; g++) {
-                cudaSetDevice(g);
-                if (cudaMemcpy(part.data() + nrec * g, d_part[g], nrec * sizeof(hpgv_epi_model_t), cudaMemcpyDeviceToHost) != cudaSuccess)
-                    LOGF("GPU %d: copy of the ranking failed\n", g);
-                cudaFree(d_part[g]);
+                if (rcs[g] != HPGV_OK) LOGF("GPU %d: %s\n", g, hpgv_epi_last_error(ctx[g]));
                 LOGI("Range finished: GPU %d\n", g);
             }
-            cudaSetDevice(0);
-            hpgv_epi_model_t *d_all = nullptr, *d_out = nullptr;
-            if (cudaMalloc((void **) &d_all, part.size() * sizeof(hpgv_epi_model_t)) != cudaSuccess ||
-                cudaMalloc((void **) &d_out, nrec * sizeof(hpgv_epi_model_t)) != cudaSuccess) LOGF("GPU 0: out of memory\n");
-            cudaMemcpy(d_all, part.data(), part.size() * sizeof(hpgv_epi_model_t), cudaMemcpyHostToDevice);
-            if (hpgv_epi_merge_device(ctx[0], order, opt->eval_subset, ngpu, num_folds, rank, d_all, d_out) != HPGV_OK)
+            if (hpgv_epi_merge_host(ctx[0], order, opt->eval_subset, ngpu, num_folds, rank, part.data(), models.data()) != HPGV_OK)
                 LOGF("GPU 0: %s\n", hpgv_epi_last_error(ctx[0]));
-            if (cudaMemcpy(models.data(), d_out, nrec * sizeof(hpgv_epi_model_t), cudaMemcpyDeviceToHost) != cudaSuccess)
-                LOGF("GPU 0: copy of the merged ranking failed\n");
-            cudaFree(d_all);
-            cudaFree(d_out);
         }
         const int nrows = hpgv_epi_merge_rankings(order, num_folds, rank, models.data(), opt->eval_mode, rows.data(), (int) rows.size());
 
@@ -399,7 +394,7 @@ extern "C" int run_epistasis(shared_options_data_t *shared, epistasis_options_da
 namespace {
 
 struct EpiOptions {
-    std::string dataset, outdir, config, eval_subset, eval_mode;
+    std::string dataset, outdir, outfile, eval_subset, eval_mode, eval_function;
     bool has_dataset = false, has_order = false, has_subset = false, has_mode = false;
     long order = 0, stride = 0, num_folds = 0, num_cv = 0, rank = 0, threads = 0, seed = 0, gpus = 0;
     bool has_seed = false;
@@ -476,7 +471,7 @@ bool read_epistasis_config(const char *path, std::map<std::string, std::string> 
 void usage() {
     printf("Usage: hpg-var-gwas epi -d|--dataset=<file> [--outdir=<str>] --order=<int> [--num-folds=<int>] [--num-cv-runs=<int>]\n"
            "                        [--rank-size=<int>] [--eval-subset=<str>] [--eval-mode=<str>] [--stride=<int>] [-c|--config=<file>]\n"
-           "                        [--num-threads=<int>] [--seed=<int>] [--gpus=<int>]\n"
+           "                        [--num-threads=<int>] [--seed=<int>] [--gpus=<int>] [--eval-function=<str>] [--out=<file>] [-l|--log-level=<str>]\n"
            "  -d, --dataset=<file>   Binary dataset used as input\n"
            "  --outdir=<str>         Directory where the output files will be stored\n"
            "  --order=<int>          Number of SNPs to be combined at the same time\n"
@@ -489,7 +484,10 @@ void usage() {
            "  -c, --config=<file>    File that contains the parameters for configuring the application\n"
            "  --num-threads=<int>    Number of threads when a task runs in parallel (host side only)\n"
            "  --seed=<int>           Draw reproducible folds (repetition r uses seed + r); default: microsecond clock\n"
-           "  --gpus=<int>           Number of GPUs of this box to shard the combination space over (default 1)\n");
+           "  --gpus=<int>           Number of GPUs of this box to shard the combination space over (default 1)\n"
+           "  --eval-function=<str>  Function that scores a model: ba (default, what the reference uses), ca, gamma, tau-b\n"
+           "  --out=<file>           Name of the report file inside --outdir (default hpg-variant.cv<N>.epi)\n"
+           "  -l, --log-level=<str>  Level of the messages to log (debug, info, warn, error, fatal, nothing)\n");
 }
 
 }  // namespace
@@ -539,10 +537,10 @@ extern "C" int epistasis(int argc, char *argv[], const char *configuration_file)
             const size_t eq = arg.find('=');
             name = arg.substr(2, eq == std::string::npos ? std::string::npos : eq - 2);
             if (eq != std::string::npos) { value = arg.substr(eq + 1); has_value = true; }
-        } else if (arg == "-d" || arg == "-c") {
-            name = arg == "-d" ? "dataset" : "config";
-        } else if (arg.rfind("-d", 0) == 0 || arg.rfind("-c", 0) == 0) {
-            name = arg[1] == 'd' ? "dataset" : "config";
+        } else if (arg == "-d" || arg == "-c" || arg == "-l") {
+            name = arg == "-d" ? "dataset" : (arg == "-c" ? "config" : "log-level");
+        } else if (arg.rfind("-d", 0) == 0 || arg.rfind("-c", 0) == 0 || arg.rfind("-l", 0) == 0) {
+            name = arg[1] == 'd' ? "dataset" : (arg[1] == 'c' ? "config" : "log-level");
             value = arg.substr(2); has_value = true;
         } else {
             printf("hpg-var-gwas: unexpected argument \"%s\"\n", arg.c_str());
@@ -560,7 +558,16 @@ extern "C" int epistasis(int argc, char *argv[], const char *configuration_file)
         };
         if (name == "dataset") { o.dataset = value; o.has_dataset = true; }
         else if (name == "outdir") o.outdir = value;
-        else if (name == "config") o.config = value;
+        else if (name == "config") {}                          // read by the front-end before epistasis() is called (main_gwas.c:58-66)
+        else if (name == "out") o.outfile = value;             // shared option (shared_options.c:30); not in the reference's epi table, accepted here
+        else if (name == "log-level") {                        // shared option (shared_options.c:58), same
+            static const char *levels[] = {"debug", "info", "warn", "error", "fatal"};
+            bool ok = false;
+            for (int l = 0; l < 5; l++) if (value == levels[l] || value == std::to_string(l + 1)) { g_log_level = l + 1; ok = true; }
+            if (value == "nothing") { g_log_level = LV_FATAL + 1; ok = true; }
+            if (!ok) { printf("hpg-var-gwas: invalid argument \"%s\" to option --log-level\n", value.c_str()); errors++; }
+        }
+        else if (name == "eval-function") o.eval_function = value;
         else if (name == "order") { as_long(o.order); o.has_order = true; }
         else if (name == "num-folds") as_long(o.num_folds);
         else if (name == "num-cv-runs") as_long(o.num_cv);
@@ -573,7 +580,9 @@ extern "C" int epistasis(int argc, char *argv[], const char *configuration_file)
         else if (name == "gpus") as_long(o.gpus);
         else { printf("hpg-var-gwas: invalid option \"%s\"\n", arg.c_str()); errors++; }
     }
-    (void) errors;   // like the reference, parse errors are printed and verification decides (epistasis_options_parsing.c:105-112)
+    // Like the reference, parse errors are printed and verification decides (parse_epistasis_options prints arg_print_errors
+    // and returns, epistasis_options_parsing.c:105-112; main_epistasis.c:62-70 goes on to verify_epistasis_options).
+    if (errors) LOGW("%d command-line argument(s) could not be understood (see above); continuing with the rest like the reference\n", errors);
 
     // Step 3: verification, with the reference's messages and codes (epistasis_options_parsing.c:143-182)
     if (!o.has_dataset) { LOGE("Please specify the dataset file.\n"); return EPISTASIS_DATASET_NOT_SPECIFIED; }
@@ -591,6 +600,8 @@ extern "C" int epistasis(int argc, char *argv[], const char *configuration_file)
     memset(&shared, 0, sizeof shared);
     std::string outdir = o.outdir;
     shared.output_directory = outdir.empty() ? nullptr : &outdir[0];
+    std::string outfile = o.outfile;
+    shared.output_filename = outfile.empty() ? nullptr : &outfile[0];
     shared.num_threads = (int) o.threads;
     epistasis_options_data_t opt;
     memset(&opt, 0, sizeof opt);
@@ -605,6 +616,14 @@ extern "C" int epistasis(int argc, char *argv[], const char *configuration_file)
     opt.eval_mode = (o.has_mode && o.eval_mode == "count") ? CV_C : CV_A;
     if (o.has_seed) setenv("HPGV_EPI_SEED", std::to_string(o.seed).c_str(), 1);
     if (o.gpus > 0) setenv("HPGV_EPI_GPUS", std::to_string(o.gpus).c_str(), 1);
+    if (!o.eval_function.empty()) {
+        // extension: which of evaluate_model's functions ranks the models; the reference's runner hard-wires BA (model.c:331)
+        static const struct { const char *name; int code; } fns[] = {{"ba", HPGV_EVAL_BA}, {"ca", HPGV_EVAL_CA_TRUE}, {"gamma", HPGV_EVAL_GAMMA}, {"tau-b", HPGV_EVAL_TAU_B}};
+        int code = -1;
+        for (auto &f : fns) if (o.eval_function == f.name) code = f.code;
+        if (code < 0) { LOGE("Unknown evaluation function '%s' (ba, ca, gamma, tau-b)\n", o.eval_function.c_str()); return EPISTASIS_EVAL_MODE_NOT_SPECIFIED; }
+        setenv("HPGV_EPI_EVAL_FUNCTION", std::to_string(code).c_str(), 1);
+    }
 
     // Step 5
     run_epistasis(&shared, &opt);

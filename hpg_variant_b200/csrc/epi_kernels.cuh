@@ -121,8 +121,10 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const uint8_t *__restric
         const uint8_t *src = raw + snp0 * nsamples;
         const int64_t nbytes = (int64_t) nr * nsamples;
         const int mis = (int) (reinterpret_cast<uintptr_t>(src) & 15);
-        // a 16-byte group may reach outside the matrix at its two ends: those rows are read bytewise
-        if ((snp0 + nr < nv || ((nbytes + mis) & 15) == 0) && (snp0 > 0 || mis == 0)) {
+        // a 16-byte group may reach up to 15 bytes outside the batch at either end: it must still lie inside the matrix
+        // (whose ends are only byte aligned: a caller-owned device pointer), else the rows are read bytewise
+        const int64_t before = snp0 * nsamples, after = (nv - snp0 - nr) * nsamples;
+        if ((after >= 15 || ((nbytes + mis) & 15) == 0) && before >= mis) {
             const uint4 *src16 = reinterpret_cast<const uint4 *>(src - mis);
             const int n16 = (int) ((nbytes + mis + 15) / 16);
             for (int x = tid; x < n16; x += blockDim.x) reinterpret_cast<uint4 *>(row_s)[x] = __ldg(src16 + x);
@@ -182,6 +184,45 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const uint8_t *__restric
             }
         }
         __syncthreads();
+    }
+}
+
+// The samples every SNP is missing (in no plane although the bit position holds a sample), as a list of at most mcap - 1
+// entries per SNP followed by kMissEnd (see search3v2_kernel for the entry format); rows past the last SNP get empty lists.
+// One warp per SNP.  miss == nullptr: only the longest list's length is computed (max_cnt).
+__global__ void miss_list_kernel(const uint8_t *__restrict__ raw, int64_t nv, int64_t nrows, int64_t nsamples, const int32_t *__restrict__ perm,
+                                 const FoldLayout *__restrict__ flp, const uint16_t *__restrict__ blk_desc, int64_t npos, int mcap,
+                                 uint32_t *__restrict__ miss, int *__restrict__ max_cnt) {
+    const FoldLayout &fl = *flp;
+    const int lane = threadIdx.x & 31;
+    const int64_t snp = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (snp >= nrows) return;
+    const int bw = fl.bw, cb = fl.cb;
+    int cnt = 0;
+    if (snp < nv) {
+        for (int64_t p0 = 0; p0 < npos; p0 += 32) {
+            const int64_t pos = p0 + lane;
+            const int32_t col = pos < npos ? perm[pos] : -1;
+            const bool is_missing = col >= 0 && raw[snp * nsamples + col] > 2;
+            const unsigned m = __ballot_sync(0xffffffffu, is_missing);
+            if (is_missing && miss) {
+                const int idx = cnt + __popc(m & ((1u << lane) - 1u));
+                if (idx < mcap - 1) {
+                    const int b = (int) (pos / (32 * bw)), w = (int) ((pos / 32) % bw), bit = (int) (pos & 31);
+                    const int ch = b / cb, off = (b % cb) * 3 * bw + w;
+                    uint32_t code;
+                    if (fl.single) code = (uint32_t) (b >> 2) | ((uint32_t) (b & 3) << 10);
+                    else { const int seg = blk_desc[b] & 0x7fff; code = (uint32_t) (seg >> 1) | ((uint32_t) (seg & 1) << 5); }
+                    miss[snp * mcap + idx] = ((uint32_t) bit << 27) | ((uint32_t) off << 16) | ((uint32_t) ch << 12) | code;
+                }
+            }
+            cnt += __popc(m);
+        }
+    }
+    if (miss) {
+        for (int x = min(cnt, mcap - 1) + lane; x < mcap; x += 32) miss[snp * mcap + x] = 0xFFFFFFFFu;
+    } else if (lane == 0) {
+        atomicMax(max_cnt, cnt);
     }
 }
 
@@ -1421,6 +1462,334 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3_kernel(const Search
                 else epilogue_general<27, SINGLE>(ctl, a, lists, cnts, nwc, nthreads, valid, i, j, k, lane);
             }
         }
+    }
+    search_publish(ctl, a, lists);
+}
+
+// ============================================================================
+// Order 3, resident (j, k) tiles and streamed i rows
+// ============================================================================
+// unit = (tile of TJ j rows, tile of 32 k rows); the rows of the tile -- every chunk of them -- stay in shared memory while
+// the i rows (i < j) stream through a ring of stages, NI of them per step.  Two warps share a j: warp (ga, jw), ga in {0, 1},
+// lane <-> k, so a thread counts the NINE cells (ga, gb, gc) of one triple and the pair of threads (0, jw, lane), (1, jw, lane)
+// covers the 18 cells of i's genotypes 0 and 1.  The cells of genotype 2 of SNP i are not counted:
+//     n(2, gb, gc) = n_jk(gb, gc) - n(0, gb, gc) - n(1, gb, gc) - n(i missing, gb, gc)
+// with n_jk the pair table of (j, k), counted once per unit (it is the same for every i).  The last term is sparse: the
+// packer lists the handful of samples every SNP is missing (miss_list_kernel); before the pair of threads evaluates a triple
+// the ga = 0 thread takes SNP i's missing samples out of the pair table, one shared-memory atomic each, and the ga = 1 thread
+// puts them back afterwards.  A third of the AND / carry-save / POPC work of the plain kernel is gone, 27 x F counter words
+// per triple become 9 x F per thread (twice the warps fit an SM), and the j and k planes are read from HBM/L2 once per unit
+// instead of once per i.  After the counts the two threads meet at a named barrier (64 threads), split the folds between
+// them and evaluate them from the three tables; a second barrier keeps the next i's counts off tables that are still read.
+struct Smem3Map {
+    size_t tile, ring0, stage_bytes, stage_rows_bytes, counters, njk, desc, lists, total;
+};
+__host__ __device__ inline Smem3Map search3v2_smem_map(const FoldLayout &fl, int tj, int ni, int nstages, int mcap, int rank, bool lists_in_smem) {
+    Smem3Map m;
+    const size_t snp_bytes = (size_t) fl.nchunks * fl.row_words * 4;              // every chunk of one SNP
+    m.tile = align_up(sizeof(SearchCtl), 128);
+    m.ring0 = m.tile + align_up((size_t) (tj + kTileJ) * snp_bytes, 128);
+    m.stage_rows_bytes = (size_t) ni * snp_bytes;
+    m.stage_bytes = align_up(m.stage_rows_bytes + (size_t) ni * mcap * 4, 128);
+    m.counters = m.ring0 + (size_t) nstages * m.stage_bytes;
+    const int nwc = fl.single ? fl.nblocks / 4 : fl.F;
+    const size_t slice = (size_t) counter_stride(9, nwc) * 4;
+    m.njk = m.counters + slice * (size_t) (2 * tj * 32);
+    m.desc = m.njk + slice * (size_t) (tj * 32);
+    m.lists = align_up(m.desc + (fl.single ? 0 : (size_t) fl.nblocks * 2), 16);
+    m.total = m.lists + (lists_in_smem ? (size_t) fl.F * rank * sizeof(Cand) : 0);
+    return m;
+}
+
+// entry of a SNP's list of missing samples (made by miss_list_kernel): where the sample sits in a chunk row and which
+// counter it belongs to.  0xFFFFFFFF ends the list.
+//   [31:27] bit   [26:16] word offset inside the chunk row: (block in chunk * 3) * slot words + word   [15:12] chunk
+//   [11:0]  counter: 16-bit counters: fold | class << 5;  byte counters: word (block / 4) | (block & 3) << 10
+constexpr uint32_t kMissEnd = 0xFFFFFFFFu;
+
+__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+// in-fold count pair (cases | controls << 16) of fold f from a counter word
+template <bool U8>
+__device__ __forceinline__ uint32_t fold_pair(uint32_t w, int f) {
+    if constexpr (U8) return __byte_perm(w, 0u, (f & 1) ? 0x4341 : 0x4240);
+    else return w;
+}
+
+template <int BW, bool SINGLE, bool BALANCED>
+__global__ void __launch_bounds__(kMaxWarps * 32, 1) search3v2_kernel(const SearchArgs a) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    SearchCtl *ctl = reinterpret_cast<SearchCtl *>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nwarps = blockDim.x >> 5, TJ = nwarps >> 1;
+    const int ga = warp / TJ, jw = warp - ga * TJ;               // warps [0, TJ): genotype 0 of SNP i, [TJ, 2 TJ): genotype 1'
+    const int NI = a.v2_ni, NS = a.nstages;
+    const Smem3Map sm = search3v2_smem_map(*a.fl, TJ, NI, NS, a.v2_mcap, a.rank, a.lists_in_smem != 0);
+    uint32_t *cnt_base = reinterpret_cast<uint32_t *>(smem_raw + sm.counters);
+    uint16_t *desc = reinterpret_cast<uint16_t *>(smem_raw + sm.desc);
+    Cand *lists = a.lists_in_smem ? reinterpret_cast<Cand *>(smem_raw + sm.lists) : a.lists + (size_t) blockIdx.x * a.fl->F * a.rank;
+    search_init<SINGLE>(ctl, a, cnt_base, (sm.desc - sm.counters) / 4, desc);      // (barriers: full/empty[0..1] = the ring, full[2] = the tile)
+    constexpr int SW = slot_words(BW);
+    const int nblocks = ctl->fl.nblocks, cb = ctl->fl.cb, nchunks = ctl->fl.nchunks, roww = ctl->fl.row_words, F = ctl->fl.F;
+    const int nwc = SINGLE ? nblocks / 4 : F;
+    const int stride = counter_stride(9, nwc);
+    const uint32_t row_bytes = (uint32_t) roww * 4;
+    const int tile_rows = TJ + kTileJ;
+
+    // ---- step sequencing (lane 0 of the last warp): unit -> groups of NI i rows ----
+    // meta: x = first i of the group (-1: no more work), y = j0, z = k0, w = number of i rows of this group | new unit << 16
+    long long u = blockIdx.x;
+    int cur_j0 = 0, cur_k0 = 0, cur_i = 0, cur_iend = 0;
+    bool fresh = false;
+    auto decode = [&]() {
+        const int2 d = __ldg(a.unit_desc + u);
+        cur_j0 = d.x; cur_k0 = d.y;
+        cur_i = a.edge_lo;                                         // first SNP of the range's first triple
+        cur_iend = min(a.edge_hi, min(cur_j0 + TJ - 2, a.nv - 3)) + 1;   // i < j <= j0 + TJ - 1, and inside the range
+        fresh = true;
+    };
+    auto next_desc = [&]() {
+        for (;;) {
+            if (u >= a.num_units) return make_int4(-1, 0, 0, 0);
+            if (cur_i < cur_iend) {
+                const int n = min(NI, cur_iend - cur_i);
+                const int4 d = make_int4(cur_i, cur_j0, cur_k0, n | (fresh ? 1 << 16 : 0));
+                cur_i += n; fresh = false;
+                return d;
+            }
+            u += gridDim.x;
+            if (u < a.num_units) decode();
+        }
+    };
+    auto issue_tile = [&](int j0, int k0) {
+        uint8_t *dst = smem_raw + sm.tile;
+        mbar_arrive_expect_tx(&ctl->full[2], (uint32_t) nchunks * tile_rows * row_bytes);
+        for (int ch = 0; ch < nchunks; ch++) {
+            const char *src = reinterpret_cast<const char *>(a.planes) + (int64_t) ch * a.snp_pad * row_bytes;
+            bulk_g2s(dst + (size_t) ch * tile_rows * row_bytes, src + (int64_t) j0 * row_bytes, (uint32_t) TJ * row_bytes, &ctl->full[2]);
+            bulk_g2s(dst + ((size_t) ch * tile_rows + TJ) * row_bytes, src + (int64_t) k0 * row_bytes, (uint32_t) kTileJ * row_bytes, &ctl->full[2]);
+        }
+    };
+    auto issue_rows = [&](int st, int i0) {                         // always NI rows: the planes are padded past the last SNP
+        uint8_t *dst = smem_raw + sm.ring0 + (size_t) st * sm.stage_bytes;
+        mbar_arrive_expect_tx(&ctl->full[st], (uint32_t) (nchunks * NI) * row_bytes + (uint32_t) (NI * a.v2_mcap * 4));
+        for (int ch = 0; ch < nchunks; ch++) {
+            const char *src = reinterpret_cast<const char *>(a.planes) + (int64_t) ch * a.snp_pad * row_bytes;
+            bulk_g2s(dst + (size_t) ch * NI * row_bytes, src + (int64_t) i0 * row_bytes, (uint32_t) NI * row_bytes, &ctl->full[st]);
+        }
+        bulk_g2s(dst + sm.stage_rows_bytes, a.v2_miss + (int64_t) i0 * a.v2_mcap, (uint32_t) (NI * a.v2_mcap * 4), &ctl->full[st]);
+    };
+    const bool producer = (tid == blockDim.x - 32);
+    if (producer) {
+        if (u < a.num_units) decode();
+        const int4 d = next_desc();
+        ctl->meta[0] = d;
+        if (d.x >= 0) { issue_tile(d.y, d.z); issue_rows(0, d.x); }
+        else mbar_arrive(&ctl->full[0]);
+    }
+
+    uint32_t *mine = cnt_base + (size_t) ((ga * TJ + jw) * 32 + lane) * stride;          // this thread's nine cells
+    const uint32_t *tab0 = cnt_base + (size_t) ((0 * TJ + jw) * 32 + lane) * stride;     // n(0, ., .)  of the triple
+    const uint32_t *tab1 = cnt_base + (size_t) ((1 * TJ + jw) * 32 + lane) * stride;     // n(1, ., .)
+    uint32_t *tabjk = reinterpret_cast<uint32_t *>(smem_raw + sm.njk) + (size_t) (jw * 32 + lane) * stride;   // n_jk(., .)
+    const uint32_t *tile = reinterpret_cast<const uint32_t *>(smem_raw + sm.tile);
+    const int fsplit = (F + 1) >> 1;                                  // folds [0, fsplit): the ga = 0 thread, the rest: its partner
+    const int f_lo = ga == 0 ? 0 : fsplit, f_hi = ga == 0 ? fsplit : F;
+    const RiskParams rp = risk_params(ctl->fl);
+    uint32_t tile_phase = 0;
+
+    // counts the nine cells pi x (gb, gc) of every block into dst (pi = plane `mode` of SNP i; mode 2: no pi, the pair table)
+    auto count_tables = [&](const uint32_t *irows, int istride, int mode, uint32_t *dst) {
+        uint32_t acc[9];
+#pragma unroll
+        for (int c = 0; c < 9; c++) acc[c] = 0;
+        for (int ch = 0; ch < nchunks; ch++) {
+            const uint32_t *jr = tile + ((size_t) ch * tile_rows + jw) * roww;
+            const uint32_t *kr = tile + ((size_t) ch * tile_rows + TJ + lane) * roww;
+            const uint32_t *ir = irows + (size_t) ch * istride;
+            const int b_lo = ch * cb, b_hi = min(nblocks, b_lo + cb);
+            for (int b = b_lo; b < b_hi; b++) {
+                const int off = (b - b_lo) * 3 * SW;
+                uint32_t pl[3][BW], pi[BW];
+#pragma unroll
+                for (int g = 0; g < 3; g++) load_plane<BW>(kr + off + g * SW, pl[g]);
+                if (mode != 2) load_plane<BW>(ir + off + mode * SW, pi);
+#pragma unroll
+                for (int gb = 0; gb < 3; gb++) {
+                    uint32_t pj[BW];
+                    load_plane<BW>(jr + off + gb * SW, pj);
+#pragma unroll
+                    for (int gc = 0; gc < 3; gc++) {
+                        if constexpr (SINGLE) {
+                            // byte counters, four blocks to a word: the weight of the block is its byte's unit
+                            const uint32_t kq = 1u << group_shift(b & 3);
+                            uint32_t n = 0;
+                            if (mode == 2) n = cell_count2_acc<BW, 1u>(pj, pl[gc], 0u);
+                            else n = cell_count3_acc<BW, 1u>(pi, pj, pl[gc], 0u);
+                            acc[gb * 3 + gc] += n * kq;
+                        } else {
+                            if (mode == 2) acc[gb * 3 + gc] = cell_count2_acc<BW, 1u>(pj, pl[gc], acc[gb * 3 + gc]);
+                            else acc[gb * 3 + gc] = cell_count3_acc<BW, 1u>(pi, pj, pl[gc], acc[gb * 3 + gc]);
+                        }
+                    }
+                }
+                if constexpr (SINGLE) {
+                    if ((b & 3) == 3) {
+#pragma unroll
+                        for (int c = 0; c < 9; c++) { dst[(b >> 2) * 9 + c] = acc[c]; acc[c] = 0; }
+                    }
+                } else {
+                    const unsigned d = desc[b];
+                    if (d & 0x8000u) {
+                        const int seg = d & 0x7fff;
+#pragma unroll
+                        for (int c = 0; c < 9; c++) {
+                            reinterpret_cast<uint16_t *>(dst + (seg >> 1) * 9 + c)[seg & 1] = (uint16_t) acc[c];
+                            acc[c] = 0;
+                        }
+                    }
+                }
+            }
+        }
+    };
+
+    int st = 0;
+    uint32_t ph = 0;
+    const uint32_t *miss = nullptr;                                 // the lists of the current stage's SNPs
+    // sign = -1: the samples SNP i (row ii of the stage) is missing leave the cells (j, k) puts them in; +1: they return
+    auto missing_fixup = [&](int ii, int sign) {
+        const uint32_t *ml = miss + (size_t) ii * a.v2_mcap;
+        for (int m = 0; m < a.v2_mcap; m++) {
+            const uint32_t e = ml[m];
+            if (e == kMissEnd) break;
+            const int bit = e >> 27, off = (e >> 16) & 0x7ff, ch = (e >> 12) & 0xf, code = e & 0xfff;
+            const uint32_t *jr = tile + ((size_t) ch * tile_rows + jw) * roww + off;
+            const uint32_t *kr = tile + ((size_t) ch * tile_rows + TJ + lane) * roww + off;
+            const uint32_t j1 = (jr[SW] >> bit) & 1u, j2 = (jr[2 * SW] >> bit) & 1u, jv = ((jr[0] >> bit) & 1u) | j1 | j2;
+            const uint32_t k1 = (kr[SW] >> bit) & 1u, k2 = (kr[2 * SW] >> bit) & 1u, kv = ((kr[0] >> bit) & 1u) | k1 | k2;
+            if (jv & kv) {
+                const int c = (int) (j1 + 2 * j2) * 3 + (int) (k1 + 2 * k2);
+                uint32_t delta, *word;
+                if constexpr (SINGLE) { word = tabjk + (code & 0x3ff) * 9 + c; delta = 1u << group_shift(code >> 10); }
+                else { word = tabjk + (code & 0x1f) * 9 + c; delta = 1u << (16 * (code >> 5)); }
+                atomicAdd(word, sign < 0 ? 0u - delta : delta);     // (the partner's fix-up of the previous SNP may still be under way)
+            }
+        }
+    };
+    for (uint32_t s = 0;; s++) {
+        const int nst = st + 1 == NS ? 0 : st + 1;
+        int4 next = make_int4(-1, 0, 0, 0);
+        if (producer) {
+            next = next_desc();                                     // step s + 1
+            ctl->meta[(s + 1) & 3] = next;
+            // its stage was last read by step s + 1 - NS; a new unit's tile may only land once every warp is through step s
+            if (s + 1 >= (uint32_t) NS && !(next.x >= 0 && (next.w >> 16))) mbar_wait(&ctl->empty[nst], ((s + 1 - NS) / NS) & 1);
+            if (next.x >= 0 && !(next.w >> 16)) issue_rows(nst, next.x);
+            else if (next.x < 0) mbar_arrive(&ctl->full[nst]);
+        }
+        __syncwarp();
+        mbar_wait(&ctl->full[st], ph);
+        const int4 meta = ctl->meta[s & 3];
+        if (meta.x < 0) break;
+        const int i0 = meta.x, j0 = meta.y, k0 = meta.z, ni = meta.w & 0xffff;
+        if (meta.w >> 16) {
+            // a new unit: its tile has been requested when the last step of the previous unit was done; count the pair table
+            mbar_wait(&ctl->full[2], tile_phase);
+            tile_phase ^= 1u;
+            if (ga == 0) count_tables(tile, 0, 2, tabjk);
+            pair_barrier(1 + jw);
+        }
+        // the best bound any CTA has published, every 32 steps, by a different warp each time
+        if ((s & 31) == 0 && lane < F && warp == (int) ((s >> 5) % (uint32_t) nwarps)) refresh_threshold(ctl, a, lane);
+        const uint32_t *stage = reinterpret_cast<const uint32_t *>(smem_raw + sm.ring0 + (size_t) st * sm.stage_bytes);
+        miss = reinterpret_cast<const uint32_t *>(smem_raw + sm.ring0 + (size_t) st * sm.stage_bytes + sm.stage_rows_bytes);
+        const int j = j0 + jw, k = k0 + lane;
+        for (int ii = 0; ii < ni; ii++) {
+            const int i = i0 + ii;
+            count_tables(stage + (size_t) ii * roww, NI * roww, ga, mine);
+            if (ga == 0) missing_fixup(ii, -1);                     // SNP i's missing samples leave the pair table ...
+            pair_barrier(1 + jw);                                   // both tables of the triple are complete
+
+            bool valid = (i < j) && (j < k) && (k < a.nv);
+            if (valid && (i <= a.edge_lo || i >= a.edge_hi)) {
+                const uint64_t idx = triple_index((uint64_t) a.nv, (uint64_t) i, (uint64_t) j, (uint64_t) k);
+                valid = idx >= a.first && idx < a.last;
+            }
+            if (__any_sync(0xffffffffu, valid)) {
+                // totals over the folds: cells of i's genotypes 0, 1 and (derived) 2
+                uint32_t tot[27];
+#pragma unroll
+                for (int c = 0; c < 27; c++) tot[c] = 0;
+                for (int kk = 0; kk < nwc; kk++) {
+#pragma unroll
+                    for (int c = 0; c < 9; c++) {
+                        const uint32_t w0 = tab0[kk * 9 + c], w1 = tab1[kk * 9 + c], w2 = tabjk[kk * 9 + c] - w0 - w1;
+                        if constexpr (SINGLE) {
+                            tot[c] += __dp4a(w0, 0x00000101u, 0u) | (__dp4a(w0, 0x01010000u, 0u) << 16);
+                            tot[9 + c] += __dp4a(w1, 0x00000101u, 0u) | (__dp4a(w1, 0x01010000u, 0u) << 16);
+                            tot[18 + c] += __dp4a(w2, 0x00000101u, 0u) | (__dp4a(w2, 0x01010000u, 0u) << 16);
+                        } else {
+                            tot[c] += w0; tot[9 + c] += w1; tot[18 + c] += w2;
+                        }
+                    }
+                }
+                for (int f = f_lo; f < f_hi; f++) {
+                    const int kk = SINGLE ? (f >> 1) : f;
+                    auto in_of = [&](int c) -> uint32_t {
+                        const int g = c / 9, cc = c - g * 9;
+                        const uint32_t w0 = tab0[kk * 9 + cc], w1 = tab1[kk * 9 + cc];
+                        const uint32_t w = g == 0 ? w0 : (g == 1 ? w1 : tabjk[kk * 9 + cc] - w0 - w1);
+                        return fold_pair<SINGLE>(w, f);
+                    };
+                    const int npos = a.training ? ctl->fl.A - ctl->fl.a_in[f] : ctl->fl.a_in[f];
+                    const int nneg = a.training ? ctl->fl.U - ctl->fl.u_in[f] : ctl->fl.u_in[f];
+                    const bool degenerate = (npos == 0 || nneg == 0);
+                    if constexpr (BALANCED) {
+                        if (a.prefilter) {
+                            // score / n_f = sum over the cells of max(0, trA - trU); below the fold's bound nothing can be offered
+                            int t = 0;
+#pragma unroll
+                            for (int c = 0; c < 27; c++) {
+                                const int D = dp2a_lo_us(tot[c], 0x0000FF01u, 0);
+                                t += max(dp2a_lo_us(in_of(c), 0x000001FFu, D), 0);
+                            }
+                            if (!__any_sync(0xffffffffu, valid && t >= *reinterpret_cast<volatile int *>(&ctl->tq[f]))) continue;
+                        }
+                        if (a.training) balanced_fold<27, true>(ctl, a, lists, tot, f, in_of, valid, i, j, k, lane);
+                        else balanced_fold<27, false>(ctl, a, lists, tot, f, in_of, valid, i, j, k, lane);
+                    } else {
+                        int tp = 0, fp = 0;
+                        uint32_t mask = 0;
+#pragma unroll
+                        for (int c = 0; c < 27; c++) {
+                            const uint32_t in = in_of(c);
+                            const int inA = (int) (in & 0xffffu), inU = (int) (in >> 16);
+                            const int trA = (int) (tot[c] & 0xffffu) - inA, trU = (int) (tot[c] >> 16) - inU;
+                            const bool r = high_risk(trA, trU, rp);
+                            tp += r ? (a.training ? trA : inA) : 0;
+                            fp += r ? (a.training ? trU : inU) : 0;
+                            mask |= (r ? 1u : 0u) << c;
+                        }
+                        const long long score = degenerate ? LLONG_MIN
+                                                : (a.eval_fn == kEvalBA ? ba_score(tp, fp, npos, nneg) : value_score(evaluate_fn(a.eval_fn, tp, npos - tp, fp, nneg - fp)));
+                        offer_fold(ctl, a, lists, f, valid, score, degenerate, npos, nneg, i, j, k, mask, tp, fp, lane);
+                    }
+                }
+            }
+            pair_barrier(1 + jw);                                   // the partner is done reading this thread's table
+            if (ga == 1) missing_fixup(ii, +1);                     // ... and come back
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->empty[st]);
+        if (producer && next.x >= 0 && (next.w >> 16)) {
+            // the next step starts a new unit: wait until every warp has left this one, then fetch its tile and its first rows
+            mbar_wait(&ctl->empty[st], (s / NS) & 1);
+            // (the stages of the steps before this one have been released earlier: all of the ring is free)
+            issue_tile(next.y, next.z);
+            issue_rows(nst, next.x);
+        }
+        st = nst;
+        if (st == 0) ph ^= 1u;
     }
     search_publish(ctl, a, lists);
 }

@@ -20,7 +20,8 @@ CONFIGS = {
 }
 
 
-def make_dataset(num_variants, num_affected, num_unaffected, seed, order=2, missing=0.005, planted=5, out=None):
+def make_dataset(num_variants, num_affected, num_unaffected, seed, order=2, missing=0.005, planted=5, out=None, planted_out=None):
+    """planted_out: optional list that receives the planted causal tuples (ascending SNP indices)."""
     rng = np.random.default_rng(seed)
     S = num_affected + num_unaffected
     g = out if out is not None else np.empty((num_variants, S), np.uint8)
@@ -42,6 +43,8 @@ def make_dataset(num_variants, num_affected, num_unaffected, seed, order=2, miss
     nplant = min(planted, num_variants // order)
     if nplant > 0:
         snps = rng.choice(num_variants, size=nplant * order, replace=False).reshape(nplant, order)
+        if planted_out is not None:
+            planted_out.extend(tuple(sorted(int(v) for v in tup)) for tup in snps)
         for tup in snps:
             probs = []
             for v in tup:

@@ -139,6 +139,14 @@ int hpgv_epi_search_device(hpgv_epi_ctx *ctx, int order, int eval_subset, int ra
 int hpgv_epi_merge_device(hpgv_epi_ctx *ctx, int order, int eval_subset, int num_lists, int num_folds, int rank_size,
                           const hpgv_epi_model_t *d_lists, hpgv_epi_model_t *d_out);
 
+/* The same with HOST pointers in and out (a single-process caller that drives several GPUs, e.g. run_epistasis with
+ * HPGV_EPI_GPUS > 1, hands the per-GPU results of hpgv_epi_search to the context that merges). */
+int hpgv_epi_merge_host(hpgv_epi_ctx *ctx, int order, int eval_subset, int num_lists, int num_folds, int rank_size,
+                        const hpgv_epi_model_t *lists, hpgv_epi_model_t *out);
+
+/* Number of usable CUDA devices (0 when there is none or the runtime fails: hpgv_epi_last_error(NULL) says why). */
+int hpgv_epi_device_count(void);
+
 uint64_t hpgv_epi_num_combinations(int64_t num_variants, int order);
 
 /* ---- parity hooks: per-combination dump for an explicit list of combinations.

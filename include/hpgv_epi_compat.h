@@ -74,12 +74,14 @@ typedef struct epistasis_options_data {
  * uncreatable directory, no GPU) print the reference's message and exit(1) like LOG_FATAL does.
  * Extensions, read from the environment so the struct layouts stay untouched:
  *   HPGV_EPI_SEED=<n>  deterministic folds (repetition r uses seed n + r); default: microsecond clock
- *   HPGV_EPI_GPUS=<n>  shard the combination space over n GPUs of this box (default 1) */
+ *   HPGV_EPI_GPUS=<n>  shard the combination space over n GPUs of this box (default 1), one host thread per GPU
+ *   HPGV_EPI_EVAL_FUNCTION=<code>  HPGV_EVAL_* of hpgv_epi.h that scores the models (default BA, model.c:331) */
 int run_epistasis(shared_options_data_t *shared_options_data, epistasis_options_data_t *options_data);
 
 /* src/gwas/main_gwas.h:46 (src/gwas/epistasis/main_epistasis.c:24-118): config file, then the command
  * line (-d/--dataset, --order, --stride, --num-folds, --num-cv-runs, --rank-size, --eval-subset,
- * --eval-mode, --outdir, --config, --num-threads; plus --seed and --gpus), verification with the
+ * --eval-mode, --outdir, --config, --num-threads -- the table of epistasis_options_parsing.c:115-140; plus --seed, --gpus,
+ * --eval-function and the shared --out / --log-level, which the reference's epi table leaves out), verification with the
  * reference's error codes, then run_epistasis.  Returns 0 like the reference (it ignores run_epistasis's code).
  * configuration_file == NULL applies the defaults the reference ships in etc/hpg-variant/hpg-variant.conf:36-45. */
 int epistasis(int argc, char *argv[], const char *configuration_file);

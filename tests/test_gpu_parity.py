@@ -116,6 +116,54 @@ def test_search_order3_matches_oracle(engine, oracle, nv, A, U, F, rank, subset)
     compare_models(got, want, 3)
 
 
+@pytest.mark.parametrize("nv,A,U,F,rank,missing", [
+    (40, 2000, 2000, 5, 30, 0.005),     # c4's sample axis: two 7-word blocks per segment, 16-bit counters
+    (36, 700, 700, 5, 30, 0.02),        # one 7-word block per segment, byte counters
+    (30, 400, 400, 5, 40, 0.02),        # 4-word blocks (80 per segment), byte counters
+    (28, 1300, 900, 3, 25, 0.01),       # unbalanced: the float32 risk rule, 16-bit counters
+    (26, 2600, 2600, 2, 20, 0.03),      # 1300 per segment: full 8-word blocks, long lists of missing samples
+    (24, 240, 240, 3, 3000, 0.01),      # rank > number of triples: lists in global memory, every triple comes back
+])
+def test_search_order3_resident_tiles(engine, oracle, monkeypatch, nv, A, U, F, rank, missing):
+    """search3v2_kernel ((j, k) tiles resident, genotype 2 of SNP i derived from the pair table, missing samples fixed up
+    one by one) against the oracle and against the plain order-3 kernel, whole range and a sub-range, both subsets."""
+    rng = np.random.default_rng(nv + A)
+    g = synth.make_dataset(nv, A, U, seed=nv * 13 + F, order=3, missing=missing, planted=1)
+    g[3, rng.integers(0, A + U, (A + U) // 8)] = 255          # one SNP with many missing samples
+    fos = random_folds(rng, A, U, F)
+    total = h.num_combinations(nv, 3)
+    for subset in (h.SUBSET_TRAINING, h.SUBSET_TESTING):
+        monkeypatch.delenv("HPGV_SEARCH3_V2", raising=False)
+        engine.load_dataset(g, A, U)
+        engine.set_folds(F, fos)
+        got = engine.search(3, subset, rank)
+        part = engine.search(3, subset, rank, total // 7 + 3, total // 2 + 5)
+        want, _ = oracle.search(g, A, U, 3, fos, subset, rank, threads=8, num_folds=F)
+        compare_models(got, want, 3)
+        wantp, _ = oracle.search(g, A, U, 3, fos, subset, rank, first=total // 7 + 3, last=total // 2 + 5, threads=8, num_folds=F)
+        compare_models(part, wantp, 3)
+        monkeypatch.setenv("HPGV_SEARCH3_V2", "0")
+        engine.set_folds(F, fos)
+        plain = engine.search(3, subset, rank)
+        assert plain.tobytes() == got.tobytes()
+
+
+def test_search_order3_resident_tiles_many_units(engine, monkeypatch):
+    """enough SNPs for several units per CTA and long i loops: bytes equal to the plain kernel's (c4's sample axis)."""
+    nv, A, F, rank = 300, 2000, 5, 50
+    g = synth.make_dataset(nv, A, A, seed=77, order=3, missing=0.005, planted=2)
+    fos, _ = h.k_folds(A, A, F, seed=4)
+    total = h.num_combinations(nv, 3)
+    engine.load_dataset(g, A, A)
+    engine.set_folds(F, fos)
+    got = [engine.search(3, h.SUBSET_TRAINING, rank), engine.search(3, h.SUBSET_TRAINING, rank, total // 3, total // 3 * 2 + 11)]
+    monkeypatch.setenv("HPGV_SEARCH3_V2", "0")
+    engine.set_folds(F, fos)
+    plain = [engine.search(3, h.SUBSET_TRAINING, rank), engine.search(3, h.SUBSET_TRAINING, rank, total // 3, total // 3 * 2 + 11)]
+    for a, b in zip(got, plain):
+        assert a.tobytes() == b.tobytes()
+
+
 @pytest.mark.parametrize("order,nv,A,F", [(2, 80, 600, 6), (3, 22, 240, 4)])
 def test_search_balanced_classes_uneven_folds(engine, oracle, order, nv, A, F):
     """A == U but folds that do not hold as many cases as controls: the balanced pre-filter must stand aside."""
