@@ -1598,8 +1598,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3v2_kernel(const Sear
     const RiskParams rp = risk_params(ctl->fl);
     uint32_t tile_phase = 0;
 
-    // counts the nine cells pi x (gb, gc) of every block into dst (pi = plane `mode` of SNP i; mode 2: no pi, the pair table)
-    auto count_tables = [&](const uint32_t *irows, int istride, int mode, uint32_t *dst) {
+    // counts the nine cells pi x (gb, gc) of every block into dst (pi = plane `plane` of SNP i; PAIR: no pi, the pair table).
+    // PAIR is a compile-time switch: a run-time test inside the cell loops would cut them into basic blocks of one cell
+    // each and keep the scheduler from interleaving the cells' dependent LOP3 chains.
+    auto count_tables = [&](auto pair_tag, const uint32_t *irows, int istride, int plane, uint32_t *dst) {
+        constexpr bool PAIR = decltype(pair_tag)::value;
         uint32_t acc[9];
 #pragma unroll
         for (int c = 0; c < 9; c++) acc[c] = 0;
@@ -1613,7 +1616,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3v2_kernel(const Sear
                 uint32_t pl[3][BW], pi[BW];
 #pragma unroll
                 for (int g = 0; g < 3; g++) load_plane<BW>(kr + off + g * SW, pl[g]);
-                if (mode != 2) load_plane<BW>(ir + off + mode * SW, pi);
+                if constexpr (!PAIR) load_plane<BW>(ir + off + plane * SW, pi);
 #pragma unroll
                 for (int gb = 0; gb < 3; gb++) {
                     uint32_t pj[BW];
@@ -1624,11 +1627,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3v2_kernel(const Sear
                             // byte counters, four blocks to a word: the weight of the block is its byte's unit
                             const uint32_t kq = 1u << group_shift(b & 3);
                             uint32_t n = 0;
-                            if (mode == 2) n = cell_count2_acc<BW, 1u>(pj, pl[gc], 0u);
+                            if constexpr (PAIR) n = cell_count2_acc<BW, 1u>(pj, pl[gc], 0u);
                             else n = cell_count3_acc<BW, 1u>(pi, pj, pl[gc], 0u);
                             acc[gb * 3 + gc] += n * kq;
                         } else {
-                            if (mode == 2) acc[gb * 3 + gc] = cell_count2_acc<BW, 1u>(pj, pl[gc], acc[gb * 3 + gc]);
+                            if constexpr (PAIR) acc[gb * 3 + gc] = cell_count2_acc<BW, 1u>(pj, pl[gc], acc[gb * 3 + gc]);
                             else acc[gb * 3 + gc] = cell_count3_acc<BW, 1u>(pi, pj, pl[gc], acc[gb * 3 + gc]);
                         }
                     }
@@ -1657,11 +1660,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3v2_kernel(const Sear
     uint32_t ph = 0;
     const uint32_t *miss = nullptr;                                 // the lists of the current stage's SNPs
     // sign = -1: the samples SNP i (row ii of the stage) is missing leave the cells (j, k) puts them in; +1: they return
-    auto missing_fixup = [&](int ii, int sign) {
+    auto missing_fixup = [&](int ii, int sign) {            // each thread of the pair takes every other entry, both ways
         const uint32_t *ml = miss + (size_t) ii * a.v2_mcap;
-        for (int m = 0; m < a.v2_mcap; m++) {
+        for (int m = ga; m < a.v2_mcap; m += 2) {
             const uint32_t e = ml[m];
-            if (e == kMissEnd) break;
+            if (e == kMissEnd) break;                       // (the end marker fills the list's tail: either parity meets it)
             const int bit = e >> 27, off = (e >> 16) & 0x7ff, ch = (e >> 12) & 0xf, code = e & 0xfff;
             const uint32_t *jr = tile + ((size_t) ch * tile_rows + jw) * roww + off;
             const uint32_t *kr = tile + ((size_t) ch * tile_rows + TJ + lane) * roww + off;
@@ -1696,7 +1699,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3v2_kernel(const Sear
             // a new unit: its tile has been requested when the last step of the previous unit was done; count the pair table
             mbar_wait(&ctl->full[2], tile_phase);
             tile_phase ^= 1u;
-            if (ga == 0) count_tables(tile, 0, 2, tabjk);
+            if (ga == 0) count_tables(std::true_type{}, tile, 0, 0, tabjk);
             pair_barrier(1 + jw);
         }
         // the best bound any CTA has published, every 32 steps, by a different warp each time
@@ -1706,8 +1709,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3v2_kernel(const Sear
         const int j = j0 + jw, k = k0 + lane;
         for (int ii = 0; ii < ni; ii++) {
             const int i = i0 + ii;
-            count_tables(stage + (size_t) ii * roww, NI * roww, ga, mine);
-            if (ga == 0) missing_fixup(ii, -1);                     // SNP i's missing samples leave the pair table ...
+            count_tables(std::false_type{}, stage + (size_t) ii * roww, NI * roww, ga, mine);
+            missing_fixup(ii, -1);                                  // SNP i's missing samples leave the pair table ...
             pair_barrier(1 + jw);                                   // both tables of the triple are complete
 
             bool valid = (i < j) && (j < k) && (k < a.nv);
@@ -1749,10 +1752,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3v2_kernel(const Sear
                             // score / n_f = sum over the cells of max(0, trA - trU); below the fold's bound nothing can be offered
                             int t = 0;
 #pragma unroll
-                            for (int c = 0; c < 27; c++) {
-                                const int D = dp2a_lo_us(tot[c], 0x0000FF01u, 0);
-                                t += max(dp2a_lo_us(in_of(c), 0x000001FFu, D), 0);
-                            }
+                            for (int c = 0; c < 27; c++) t += max(dp2a_lo_us(in_of(c), 0x000001FFu, dp2a_lo_us(tot[c], 0x0000FF01u, 0)), 0);
                             if (!__any_sync(0xffffffffu, valid && t >= *reinterpret_cast<volatile int *>(&ctl->tq[f]))) continue;
                         }
                         if (a.training) balanced_fold<27, true>(ctl, a, lists, tot, f, in_of, valid, i, j, k, lane);
@@ -1777,7 +1777,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3v2_kernel(const Sear
                 }
             }
             pair_barrier(1 + jw);                                   // the partner is done reading this thread's table
-            if (ga == 1) missing_fixup(ii, +1);                     // ... and come back
+            missing_fixup(ii, +1);                                  // ... and come back
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctl->empty[st]);
