@@ -630,6 +630,245 @@ extern "C" int epistasis(int argc, char *argv[], const char *configuration_file)
     return 0;
 }
 
+// -------------------------------------------------------------------------------------
+// leaf functions of model.h / mdr.h / cross_validation.h as adapters over the CUDA engine (function-level parity tests)
+// -------------------------------------------------------------------------------------
+namespace {
+
+hpgv_epi_ctx *leaf_ctx() {
+    static hpgv_epi_ctx *ctx = nullptr;
+    if (!ctx && hpgv_epi_create(0, &ctx) != HPGV_OK) LOGF("No CUDA device is available: the epistasis engine has no CPU path (%s)\n", hpgv_epi_last_error(nullptr));
+    return ctx;
+}
+#define LEAF_CK(call) do { if ((call) != HPGV_OK) LOGF("%s: %s\n", #call, hpgv_epi_last_error(leaf_ctx())); } while (0)
+
+// dataset column s (cases first) -> byte position in a padded row
+inline int padded_pos(const masks_info &info, int s) { return s < info.num_affected ? s : info.num_affected_with_padding + (s - info.num_affected); }
+
+// uploads `rows` (padded rows, one per SNP) as a data set of rows.size() variants; a single row is doubled (the engine wants >= 2)
+void leaf_load(const std::vector<const uint8_t *> &rows, const masks_info &info) {
+    const int S = info.num_affected + info.num_unaffected;
+    const size_t nv = std::max<size_t>(2, rows.size());
+    std::vector<uint8_t> g(nv * (size_t) S);
+    for (size_t v = 0; v < nv; v++) {
+        const uint8_t *row = rows[std::min(v, rows.size() - 1)];
+        for (int s = 0; s < S; s++) g[v * S + s] = row[padded_pos(info, s)];
+    }
+    LEAF_CK(hpgv_epi_load_dataset_host(leaf_ctx(), g.data(), (int64_t) nv, info.num_affected, info.num_unaffected));
+}
+
+// two folds from a byte mask over padded positions: fold 0 = masked out (the fold's own samples), fold 1 = training
+void leaf_folds(const uint8_t *fold_mask, const masks_info &info) {
+    const int S = info.num_affected + info.num_unaffected;
+    std::vector<int32_t> fos((size_t) S, 1);
+    if (fold_mask) for (int s = 0; s < S; s++) fos[s] = fold_mask[padded_pos(info, s)] ? 1 : 0;
+    LEAF_CK(hpgv_epi_set_folds(leaf_ctx(), 2, fos.data()));
+}
+
+// genotype rows back from the byte masks of one SNP ([3][S_pad]): the genotype whose mask is set, 255 where none is
+std::vector<uint8_t> row_from_masks(const uint8_t *m, const masks_info &info) {
+    const int P = info.num_samples_with_padding;
+    std::vector<uint8_t> row((size_t) P, 255);
+    for (int p = 0; p < P; p++)
+        for (int gt = 0; gt < 3; gt++) if (m[(size_t) gt * P + p]) { row[p] = (uint8_t) gt; break; }
+    return row;
+}
+
+int cell_of(const uint8_t *perm, int order) {
+    int c = 0;
+    for (int j = 0; j < order; j++) c = c * 3 + perm[j];
+    return c;
+}
+
+// TRAINING counts of fold 0 of the current 2-fold partition for the combinations (0..order-1), (order..2 order-1), ...
+void leaf_counts(int order, int ncomb, uint8_t **perms, int nperm, int *out_aff, int *out_unaff) {
+    const int C = order == 2 ? 9 : 27;
+    std::vector<int32_t> combs((size_t) ncomb * order), ca((size_t) ncomb * 2 * C), cu((size_t) ncomb * 2 * C);
+    for (int x = 0; x < ncomb * order; x++) combs[x] = x;
+    LEAF_CK(hpgv_epi_eval(leaf_ctx(), order, HPGV_SUBSET_TRAINING, ncomb, combs.data(), ca.data(), cu.data(), nullptr, nullptr, nullptr));
+    for (int rc = 0; rc < ncomb; rc++)
+        for (int p = 0; p < nperm; p++) {
+            const int c = cell_of(perms[p], order);
+            out_aff[rc * nperm + p] = ca[((size_t) rc * 2 + 0) * C + c];
+            out_unaff[rc * nperm + p] = cu[((size_t) rc * 2 + 0) * C + c];
+        }
+}
+
+}  // namespace
+
+extern "C" void masks_info_init(int order, int num_combinations_in_a_row, int num_affected, int num_unaffected, masks_info *info) {
+    info->num_affected = num_affected;
+    info->num_unaffected = num_unaffected;
+    info->num_affected_with_padding = 16 * ((num_affected + 15) / 16);
+    info->num_unaffected_with_padding = 16 * ((num_unaffected + 15) / 16);
+    info->num_combinations_in_a_row = num_combinations_in_a_row;
+    int cells = 1;
+    for (int o = 0; o < order; o++) cells *= 3;
+    info->num_cell_counts_per_combination = cells;
+    info->num_samples_with_padding = info->num_affected_with_padding + info->num_unaffected_with_padding;
+    info->num_masks = 3 * order * info->num_samples_with_padding;
+}
+
+extern "C" void set_genotypes_masks(int order, uint8_t **genotypes, int num_combinations, uint8_t *masks, masks_info info) {
+    std::vector<const uint8_t *> rows;
+    for (int x = 0; x < num_combinations * order; x++) rows.push_back(genotypes[x]);
+    leaf_load(rows, info);
+    leaf_folds(nullptr, info);
+    const size_t P = (size_t) info.num_samples_with_padding;
+    for (int x = 0; x < num_combinations * order; x++)     // [combination][snp][genotype][S_pad] is contiguous: 3 * S_pad per SNP
+        LEAF_CK(hpgv_epi_unpack_masks(leaf_ctx(), x, masks + (size_t) x * 3 * P));
+}
+
+static void leaf_load_from_masks(int order, const uint8_t *masks, const masks_info &info, std::vector<std::vector<uint8_t>> &keep) {
+    const size_t P = (size_t) info.num_samples_with_padding;
+    const int nrows = info.num_combinations_in_a_row * order;
+    keep.clear();
+    std::vector<const uint8_t *> rows;
+    for (int x = 0; x < nrows; x++) keep.push_back(row_from_masks(masks + (size_t) x * 3 * P, info));
+    for (auto &r : keep) rows.push_back(r.data());
+    leaf_load(rows, info);
+}
+
+extern "C" void combination_counts(int order, uint8_t *masks, uint8_t **genotype_combinations, int num_genotype_combinations,
+                                   int *counts_aff, int *counts_unaff, masks_info info) {
+    if (order != 2 && order != 3) LOGF("Combinations of order %d are not supported by the GPU engine (2 or 3)\n", order);
+    std::vector<std::vector<uint8_t>> keep;
+    leaf_load_from_masks(order, masks, info, keep);
+    leaf_folds(nullptr, info);                              // nobody is held out: the training table is the whole data set
+    leaf_counts(order, info.num_combinations_in_a_row, genotype_combinations, num_genotype_combinations, counts_aff, counts_unaff);
+}
+
+extern "C" void combination_counts_all_folds(int order, uint8_t *fold_masks, int num_folds, uint8_t **genotype_permutations, uint8_t *masks,
+                                             masks_info info, int *counts_aff, int *counts_unaff) {
+    if (order != 2 && order != 3) LOGF("Combinations of order %d are not supported by the GPU engine (2 or 3)\n", order);
+    std::vector<std::vector<uint8_t>> keep;
+    leaf_load_from_masks(order, masks, info, keep);
+    const int C = info.num_cell_counts_per_combination, rows = info.num_combinations_in_a_row;
+    for (int f = 0; f < num_folds; f++) {                   // the reference's fold masks need not be a partition: one 2-fold layout each
+        leaf_folds(fold_masks + (size_t) f * info.num_samples_with_padding, info);
+        leaf_counts(order, rows, genotype_permutations, C, counts_aff + (size_t) f * rows * C, counts_unaff + (size_t) f * rows * C);
+    }
+}
+
+extern "C" int *mdr_high_risk_combinations2(int *counts_affected, int *counts_unaffected, int num_counts, unsigned int num_affected,
+                                            unsigned int num_unaffected, void **aux_return_values) {
+    (void) aux_return_values;
+    const int padded = 16 * ((num_counts + 15) / 16);
+    int *flags = nullptr;
+    if (posix_memalign((void **) &flags, 16, std::max<size_t>(16, (size_t) padded * sizeof(int))) != 0) return nullptr;
+    memset(flags, 0, (size_t) padded * sizeof(int));
+    if (num_counts > 0) {
+        LEAF_CK(hpgv_epi_high_risk(leaf_ctx(), counts_affected, counts_unaffected, num_counts, (int) num_affected, (int) num_unaffected, flags));
+        for (int x = 0; x < num_counts; x++) flags[x] = flags[x] ? -1 : 0;      // what _mm_cvtps_epi32(_mm_cmpge_ps) leaves: 0x80000000 -> ... any non-zero
+    }
+    return flags;
+}
+
+extern "C" int *choose_high_risk_combinations2(unsigned int *counts_aff, unsigned int *counts_unaff, unsigned int num_combinations,
+                                               unsigned int num_counts_per_combination, unsigned int num_affected, unsigned int num_unaffected,
+                                               unsigned int *num_risky, void **aux_ret,
+                                               int *(*test_func)(int *, int *, int, unsigned int, unsigned int, void **)) {
+    (void) aux_ret; (void) test_func;
+    const int n = (int) (num_combinations * num_counts_per_combination);
+    int *flags = mdr_high_risk_combinations2((int *) counts_aff, (int *) counts_unaff, n, num_affected, num_unaffected, nullptr);
+    int *risky = (int *) malloc(std::max<size_t>(1, (size_t) n) * sizeof(int));
+    int total = 0;
+    for (int x = 0; x < n; x++)
+        if (flags[x]) { risky[total++] = x % (int) num_counts_per_combination; num_risky[x / (int) num_counts_per_combination]++; }
+    free(flags);
+    return risky;
+}
+
+extern "C" risky_combination *risky_combination_new(int order, int comb[], uint8_t **possible_genotypes_combinations, int num_risky, int *risky_idx,
+                                                    void *aux_info, masks_info info) {
+    risky_combination *r = (risky_combination *) malloc(sizeof(risky_combination));
+    r->order = order;
+    r->combination = (int *) malloc((size_t) order * sizeof(int));
+    r->cross_validation_count = 1;
+    r->accuracy = 0.0;
+    r->genotypes = (uint8_t *) malloc((size_t) info.num_cell_counts_per_combination * order);
+    r->num_risky_genotypes = num_risky;
+    r->auxiliary_info = aux_info;
+    memcpy(r->combination, comb, (size_t) order * sizeof(int));
+    for (int x = 0; x < num_risky; x++) memcpy(r->genotypes + (size_t) order * x, possible_genotypes_combinations[risky_idx[x]], (size_t) order);
+    return r;
+}
+
+extern "C" void risky_combination_free(risky_combination *combination) {
+    if (!combination) return;
+    free(combination->combination);
+    free(combination->genotypes);
+    free(combination);
+}
+
+extern "C" void confusion_matrix(int order, risky_combination *combination, uint8_t **genotypes, uint8_t *fold_masks, enum evaluation_subset subset,
+                                 int training_size[2], int testing_size[2], masks_info info, unsigned int *matrix) {
+    if (order != 2 && order != 3) LOGF("Combinations of order %d are not supported by the GPU engine (2 or 3)\n", order);
+    std::vector<const uint8_t *> rows;
+    for (int j = 0; j < order; j++) rows.push_back(genotypes[j]);
+    leaf_load(rows, info);
+    leaf_folds(fold_masks, info);
+    uint32_t mask[2] = {0, 0};
+    for (int x = 0; x < combination->num_risky_genotypes; x++) mask[0] |= 1u << cell_of(combination->genotypes + (size_t) x * order, order);
+    mask[1] = mask[0];
+    int32_t comb[3] = {0, 1, 2};
+    uint32_t conf[8];
+    LEAF_CK(hpgv_epi_confusion(leaf_ctx(), order, subset == TRAINING ? HPGV_SUBSET_TRAINING : HPGV_SUBSET_TESTING, 1, comb, mask, conf, nullptr));
+    const int *size = subset == TRAINING ? training_size : testing_size;        // fold 0 of the 2-fold layout is "this fold"
+    matrix[0] = conf[0]; matrix[2] = conf[2];
+    matrix[1] = (unsigned) size[0] - conf[0]; matrix[3] = (unsigned) size[1] - conf[2];
+}
+
+extern "C" double evaluate_model(unsigned int *confusion_matrix, enum eval_function function) {
+    double v = NAN;
+    const uint32_t m[4] = {confusion_matrix[0], confusion_matrix[1], confusion_matrix[2], confusion_matrix[3]};
+    LEAF_CK(hpgv_epi_evaluate(leaf_ctx(), (int) function, 1, m, &v));
+    return v;
+}
+
+extern "C" double test_model(int order, risky_combination *risky_comb, uint8_t **genotypes, uint8_t *fold_masks, enum evaluation_subset subset,
+                             int training_size[2], int testing_size[2], masks_info info, unsigned int *conf_matrix) {
+    confusion_matrix(order, risky_comb, genotypes, fold_masks, subset, training_size, testing_size, info, conf_matrix);
+    return evaluate_model(conf_matrix, BA);                                     // model.c:331
+}
+
+extern "C" uint8_t *get_genotypes_of_block_coord(int num_variants, int num_samples, masks_info info, int stride, int block_coord,
+                                                 uint8_t *block_start, uint8_t *genotypes) {
+    for (int x = 0; x < stride && block_coord * stride + x < num_variants; x++) {
+        uint8_t *row = genotypes + (size_t) x * info.num_samples_with_padding;
+        const uint8_t *src = block_start + (size_t) x * num_samples;
+        memset(row, 0, (size_t) info.num_samples_with_padding);
+        memcpy(row, src, (size_t) info.num_affected);
+        memcpy(row + info.num_affected_with_padding, src + info.num_affected, (size_t) info.num_unaffected);
+    }
+    return genotypes;
+}
+
+// vcf-tools/vcf2epi/dataset_creator.c:172-223 (the producer's file format, current 12-byte header)
+extern "C" int epistasis_dataset_write(const char *filename, const uint8_t *genotypes, size_t num_variants, int num_affected, int num_unaffected) {
+    FILE *fp = fopen(filename, "wb");
+    if (!fp) return -1;
+    const uint32_t hdr[3] = {(uint32_t) num_variants, (uint32_t) num_affected, (uint32_t) num_unaffected};
+    const size_t n = num_variants * (size_t) (num_affected + num_unaffected);
+    const bool ok = fwrite(hdr, sizeof hdr, 1, fp) == 1 && (n == 0 || fwrite(genotypes, 1, n, fp) == n);
+    return (fclose(fp) == 0 && ok) ? 0 : -1;
+}
+
+extern "C" uint8_t epistasis_dataset_encode_genotype(int allele1, int allele2, int alleles_missing) {
+    if (alleles_missing) return 255;
+    if (!allele1 && !allele2) return 0;
+    if (allele1 != allele2) return 1;
+    return 2;
+}
+
+extern "C" int *group_individuals_by_phenotype(uint8_t *phenotypes, int num_affected, int num_unaffected) {
+    const int n = num_affected + num_unaffected;
+    int *destination = (int *) malloc(std::max<size_t>(1, (size_t) n) * sizeof(int));
+    int a = 0, u = num_affected;
+    for (int x = 0; x < n; x++) destination[x] = phenotypes[x] ? a++ : u++;
+    return destination;
+}
+
 extern "C" void hpgv_epi_host_open_log(const char *path) {
     if (g_log_file) fclose(g_log_file);
     g_log_file = path ? fopen(path, "w") : nullptr;

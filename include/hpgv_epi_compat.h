@@ -107,6 +107,81 @@ int **get_k_folds(unsigned int samples_affected, unsigned int samples_unaffected
 uint8_t *get_k_folds_masks(unsigned int num_samples_affected, unsigned int num_samples_unaffected, unsigned int k,
                            int **folds, unsigned int *sizes);
 
+/* ---- leaf functions of the hot path, with the reference's signatures, for function-level parity tests -------------
+ * (src/gwas/epistasis/model.h:91-155, mdr.h:37-39, cross_validation.h:14-23).  With them the reference's own
+ * unit tests (test/test_epistasis_model.c) link against this library exactly as they link against the reference's
+ * objects.  They are ADAPTERS: every count, risk flag, confusion matrix and accuracy below comes from the CUDA engine
+ * (hpgv_epi_unpack_masks / hpgv_epi_eval / hpgv_epi_high_risk / hpgv_epi_confusion / hpgv_epi_evaluate on GPU 0), one
+ * small upload per call -- they are for tests, the search never goes through them. */
+
+/* model.h:49-57 */
+typedef struct {
+    double accuracy;
+    int order;
+    int num_risky_genotypes;
+    int cross_validation_count;
+    uint8_t *genotypes;
+    int *combination;
+    void *auxiliary_info;
+} risky_combination;
+
+/* model.h:60-70 */
+typedef struct {
+    int num_affected;
+    int num_unaffected;
+    int num_affected_with_padding;
+    int num_unaffected_with_padding;
+    int num_samples_with_padding;
+    int num_masks;
+    int num_combinations_in_a_row;
+    int num_cell_counts_per_combination;
+    uint8_t *masks;
+} masks_info;
+
+/* model.h:84 */
+enum eval_function { CA, BA, wBA, GAMMA, TAU_B };
+
+/* model.c:208-219 */
+void masks_info_init(int order, int num_combinations_in_a_row, int num_affected, int num_unaffected, masks_info *info);
+/* model.c:28-74: byte masks [combination][snp][genotype][S_pad], 0xFF where the sample has the genotype (GPU: pack + unpack) */
+void set_genotypes_masks(int order, uint8_t **genotypes, int num_combinations, uint8_t *masks, masks_info info);
+/* model.c:76-129 (whole data set) and model.c:131-206 (per fold, fold_masks = 1 for a training sample); counts come back as
+ * [fold][combination in the row][cell] like the reference's */
+void combination_counts(int order, uint8_t *masks, uint8_t **genotype_combinations, int num_genotype_combinations,
+                        int *counts_aff, int *counts_unaff, masks_info info);
+void combination_counts_all_folds(int order, uint8_t *fold_masks, int num_folds, uint8_t **genotype_permutations, uint8_t *masks,
+                                  masks_info info, int *counts_aff, int *counts_unaff);
+/* mdr.c:45-75: 0 / -1 flags like _mm_cmpge_ps leaves them, 16-byte aligned (free with free()) */
+int *mdr_high_risk_combinations2(int *counts_affected, int *counts_unaffected, int num_counts, unsigned int num_affected,
+                                 unsigned int num_unaffected, void **aux_return_values);
+/* model.c:226-255 with the pointer-correct callback type; the device rule decides whatever test_func is */
+int *choose_high_risk_combinations2(unsigned int *counts_aff, unsigned int *counts_unaff, unsigned int num_combinations,
+                                    unsigned int num_counts_per_combination, unsigned int num_affected, unsigned int num_unaffected,
+                                    unsigned int *num_risky, void **aux_ret,
+                                    int *(*test_func)(int *, int *, int, unsigned int, unsigned int, void **));
+/* model.c:278-296, 313-317 */
+risky_combination *risky_combination_new(int order, int comb[], uint8_t **possible_genotypes_combinations, int num_risky, int *risky_idx,
+                                         void *aux_info, masks_info info);
+void risky_combination_free(risky_combination *combination);
+/* model.c:337-460, 462-479, 324-335 */
+void confusion_matrix(int order, risky_combination *combination, uint8_t **genotypes, uint8_t *fold_masks, enum evaluation_subset subset,
+                      int training_size[2], int testing_size[2], masks_info info, unsigned int *matrix);
+double evaluate_model(unsigned int *confusion_matrix, enum eval_function function);
+double test_model(int order, risky_combination *risky_comb, uint8_t **genotypes, uint8_t *fold_masks, enum evaluation_subset subset,
+                  int training_size[2], int testing_size[2], masks_info info, unsigned int *conf_matrix);
+/* cross_validation.c:160-195: the padded copy of a block's rows (the GPU engine packs bit planes instead and never calls it) */
+uint8_t *get_genotypes_of_block_coord(int num_variants, int num_samples, masks_info info, int stride, int block_coord,
+                                      uint8_t *block_start, uint8_t *genotypes);
+
+/* vcf-tools/vcf2epi/dataset_creator.c:172-223: writes a data set in the current format (3 x uint32 header, then
+ * variant-major genotype bytes, cases first); returns 0, or -1 when the file cannot be written */
+int epistasis_dataset_write(const char *filename, const uint8_t *genotypes, size_t num_variants, int num_affected, int num_unaffected);
+/* dataset_creator.c:255-265: the byte a sample's GT becomes (0 hom-ref, 1 het, 2 hom-alt, 255 when the alleles are missing) */
+uint8_t epistasis_dataset_encode_genotype(int allele1, int allele2, int alleles_missing);
+/* dataset_creator.c:302-320: column of every sample in the data set, cases first then controls, input order kept inside a class
+ * (phenotypes[i] != 0 = affected); malloc'd, caller frees */
+int *group_individuals_by_phenotype(uint8_t *phenotypes, int num_affected, int num_unaffected);
+
 /* One ranked row of a repetition's report = what merge_rankings (epistasis.c:96-153) leaves in its heap. */
 typedef struct {
     double cv_accuracy;          /* sum of the fold accuracies / num_folds (epistasis.c:142,148) */

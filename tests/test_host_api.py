@@ -29,6 +29,11 @@ COMPAT_SYMBOLS = [
     "get_first_combination_in_block", "get_next_combination_in_block", "get_genotype_combinations",
     "get_next_genotype_combination", "get_k_folds", "get_k_folds_masks", "hpgv_epi_merge_rankings", "hpgv_epi_write_report",
     "hpgv_epi_host_open_log",
+    # leaf functions (model.h:91-155, mdr.h:37-39, cross_validation.h:14-23) and the producer side of the file format
+    "masks_info_init", "set_genotypes_masks", "combination_counts", "combination_counts_all_folds", "mdr_high_risk_combinations2",
+    "choose_high_risk_combinations2", "risky_combination_new", "risky_combination_free", "confusion_matrix", "evaluate_model",
+    "test_model", "get_genotypes_of_block_coord", "epistasis_dataset_write", "epistasis_dataset_encode_genotype",
+    "group_individuals_by_phenotype",
 ]
 
 
@@ -181,6 +186,34 @@ def test_folds_and_masks(host, oracle, monkeypatch):
     assert np.array_equal(got, oracle.fold_masks(A, U, k, fos))
 
 
+def test_dataset_writer_and_producer_helpers(host, tmp_path):
+    """SURVEY 8(f)2, the producer side (vcf-tools/vcf2epi/dataset_creator.c:172-223, 255-265, 302-320): the C writer's
+    file is what the loaders read back; genotype bytes and the cases-first column order follow the reference."""
+    rng = np.random.default_rng(3)
+    nv, A, U = 7, 5, 9
+    g = rng.choice(np.array([0, 1, 2, 255], np.uint8), size=(nv, A + U))
+    path = tmp_path / "w.bin"
+    host.epistasis_dataset_write.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
+    assert host.epistasis_dataset_write(str(path).encode(), g.ctypes.data, nv, A, U) == 0
+    raw = path.read_bytes()
+    assert struct.unpack("<III", raw[:12]) == (nv, A, U) and raw[12:] == g.tobytes()
+    g2, a2, u2 = synth.read_dataset(str(path))
+    assert (a2, u2) == (A, U) and np.array_equal(g2, g)
+    na, nu, nvar, flen, off = C.c_int(), C.c_int(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+    p = host.epistasis_dataset_load(C.byref(na), C.byref(nu), C.byref(nvar), C.byref(flen), C.byref(off), str(path).encode())
+    assert (na.value, nu.value, nvar.value, off.value) == (A, U, nv, 12)
+    assert bytes(p[off.value:off.value + nv * (A + U)]) == g.tobytes()
+    host.epistasis_dataset_close(p, flen.value)
+    assert host.epistasis_dataset_write(str(tmp_path / "no" / "dir.bin").encode(), g.ctypes.data, nv, A, U) == -1
+    host.epistasis_dataset_encode_genotype.restype = C.c_uint8
+    enc = host.epistasis_dataset_encode_genotype
+    assert [enc(0, 0, 0), enc(0, 1, 0), enc(1, 0, 0), enc(1, 1, 0), enc(2, 2, 0), enc(1, 2, 0), enc(0, 0, 1)] == [0, 1, 1, 2, 2, 1, 255]
+    host.group_individuals_by_phenotype.restype = C.POINTER(C.c_int)
+    ph = np.array([0, 1, 1, 0, 0, 1, 0], np.uint8)
+    dest = host.group_individuals_by_phenotype(ph.ctypes.data_as(C.POINTER(C.c_uint8)), 3, 4)
+    assert [dest[x] for x in range(7)] == [3, 0, 1, 4, 5, 2, 6]
+
+
 # ---- merge_rankings + report ---------------------------------------------------------------------------
 def py_merge(models, order, num_folds, mode):
     """independent restatement of merge_rankings + the report order"""
@@ -331,6 +364,75 @@ def test_cli_end_to_end_matches_oracle(oracle, tmp_path, order, nv, A, U, F, mod
         models["risky_mask"] = want["risky_mask"]
         text = (out / f"hpg-variant.cv{r + 1}.epi").read_text()
         assert text == py_report(py_merge(models, order, F, mode), order, r, mode, subset, rank)
+
+
+@pytest.mark.gpu
+def test_reference_unit_tests_pass_against_the_product():
+    """The reference's own test/test_epistasis_model.c (7 tests: byte masks, count tables whole and per fold for order 2
+    and 3, confusion matrices, evaluation formulas), compiled against the reference's headers and linked against
+    libhpgv_epi_host.so: the leaf functions it calls are the adapters over the CUDA engine (include/hpgv_epi_compat.h).
+    The binary is built where the reference's sources are (make -C oracle product-test) and travels with the snapshot."""
+    exe = os.path.join(os.path.dirname(PKG), "oracle", "_ref", "test_model_product")
+    if not os.path.exists(exe):
+        if os.path.isdir("/root/reference"):
+            subprocess.run(["make", "-s", "-C", os.path.join(os.path.dirname(PKG), "oracle"), "product-test"], check=True,
+                           env={k: v for k, v in os.environ.items() if k not in ("CC", "CXX")})
+        else:
+            pytest.skip("oracle/_ref/test_model_product not built and /root/reference absent")
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
+    assert "7 tests, 0 failed" in p.stderr
+
+
+@pytest.mark.gpu
+def test_cli_two_gpus_equal_one(tmp_path):
+    """run_epistasis with HPGV_EPI_GPUS / --gpus 2 (one host thread per GPU, contiguous index ranges, merge on GPU 0) writes
+    the bytes of the single-GPU run."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    nv, A, U, F = 300, 400, 400, 5
+    g = synth.make_dataset(nv, A, U, seed=11, missing=0.01, planted=2)
+    data = tmp_path / "d.bin"
+    synth.write_dataset(str(data), g, A, U)
+    outs = []
+    for gpus in (1, 2):
+        out = tmp_path / f"out{gpus}"
+        cmd = [CLI, "epi", "-d", str(data), "--order", "2", "--num-folds", str(F), "--num-cv-runs", "2", "--rank-size", "20",
+               "--eval-subset", "training", "--eval-mode", "accu", "--outdir", str(out), "--seed", "5", "--stride", "50", "--gpus", str(gpus)]
+        res = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stderr + res.stdout
+        if gpus == 2:
+            assert "Range finished: GPU 1" in res.stdout
+        outs.append([(out / f"hpg-variant.cv{r}.epi").read_text() for r in (1, 2)])
+    assert outs[0] == outs[1]
+
+
+@pytest.mark.gpu
+def test_cli_eval_function_and_out_options(oracle, tmp_path):
+    """--eval-function and the shared --out option through the CLI: gamma-ranked report == oracle."""
+    nv, A, U, F, rank = 40, 150, 170, 4, 12
+    g = synth.make_dataset(nv, A, U, seed=21, missing=0.01, planted=2)
+    data = tmp_path / "d.bin"
+    synth.write_dataset(str(data), g, A, U)
+    out = tmp_path / "out"
+    cmd = [CLI, "epi", "-d", str(data), "--order", "2", "--num-folds", str(F), "--num-cv-runs", "1", "--rank-size", str(rank), "--eval-subset", "training",
+           "--eval-mode", "accu", "--outdir", str(out), "--seed", "9", "--stride", "10", "--eval-function", "gamma", "--out", "gamma.epi", "-l", "warn"]
+    res = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr + res.stdout
+    assert "Running cross-validation" not in res.stdout           # --log-level warn silences the INFO lines
+    fos, _ = h.k_folds(A, U, F, 9)
+    oracle.set_eval_function(h.EVAL_GAMMA)
+    try:
+        want, _ = oracle.search(g, A, U, 2, fos, 1, rank, threads=4, num_folds=F)
+    finally:
+        oracle.set_eval_function(h.EVAL_BA)
+    models = np.zeros((F, rank), h.MODEL_DTYPE)
+    models["snp"][..., :2] = want["snp"][..., :2]
+    models["snp"][..., 2:] = -1
+    models["accuracy"] = want["ba"]
+    models["risky_mask"] = want["risky_mask"]
+    assert (out / "gamma.epi").read_text() == py_report(py_merge(models, 2, F, "accu"), 2, 0, "accu", "training", rank)
 
 
 @pytest.mark.gpu
