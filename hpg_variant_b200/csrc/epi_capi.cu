@@ -23,9 +23,24 @@ static_assert(sizeof(hpgv_epi_model_t) == 40, "hpgv_epi_model_t must be 40 bytes
 static_assert(sizeof(ModelOut) == sizeof(hpgv_epi_model_t), "device/host model records differ");
 static_assert(kMaxFolds == HPGV_MAX_FOLDS && kMaxRank == HPGV_MAX_RANK, "limits out of sync with hpgv_epi.h");
 
+#include <unistd.h>
+
 namespace {
 
 thread_local std::string g_create_error;
+
+// cudaGetDeviceCount with a few retries: right after another process of the same box has torn its context down the first
+// call of a fresh process occasionally fails with cudaErrorInitializationError (seen on multi-GPU boxes)
+cudaError_t device_count_retry(int *n) {
+    cudaError_t e = cudaSuccess;
+    for (int attempt = 0; attempt < 5; attempt++) {
+        e = cudaGetDeviceCount(n);
+        if (e == cudaSuccess) return e;
+        (void) cudaGetLastError();
+        usleep(200 * 1000);
+    }
+    return e;
+}
 
 template <typename T>
 struct DevBuf {
@@ -140,7 +155,7 @@ extern "C" int hpgv_epi_create(int device, hpgv_epi_ctx **out) {
     if (!out) return HPGV_E_ARG;
     *out = nullptr;
     int ndev = 0;
-    cudaError_t e = cudaGetDeviceCount(&ndev);
+    cudaError_t e = device_count_retry(&ndev);
     if (e != cudaSuccess || ndev == 0) {
         g_create_error = std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
                          " (this library has no CPU fallback)";
@@ -957,7 +972,7 @@ extern "C" int hpgv_epi_merge_host(hpgv_epi_ctx *ctx, int order, int eval_subset
 
 extern "C" int hpgv_epi_device_count(void) {
     int n = 0;
-    const cudaError_t e = cudaGetDeviceCount(&n);
+    const cudaError_t e = device_count_retry(&n);
     if (e != cudaSuccess) { g_create_error = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e); return 0; }
     return n;
 }
