@@ -507,7 +507,7 @@ def roofline_of(runner, r, name, peaks, popc_peak, alu_peak):
     roof = {
         "bound": "int_popc", "kernel": f"search{order}_kernel", "achieved": achieved / 1e12, "peak": popc_peak / 1e12, "unit": "TPOPC32/s",
         "frac": achieved / popc_peak, "traffic": kc.get("dram_bytes_per_launch") if kc and runner.world == 1 else None,
-        "traffic_source": kc.get("source") if kc and runner.world == 1 else None,
+        "traffic_source": (kc.get("traffic_source") or kc.get("source")) if kc and runner.world == 1 else None,
         "algorithmic": f"3^{order} x W = {popc_per_comb} POPC32 per combination (W = {Wwords} words), {my_combs} combinations per launch",
         "peak_source": "POPC micro-benchmark in this run (hpgv_epi_pipe_peak), all SMs",
         "kernel_ms": k_ms, "kernel_share_of_step": k_ms / r["my_step_ms"],

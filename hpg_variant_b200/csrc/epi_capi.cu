@@ -113,6 +113,7 @@ struct hpgv_epi_ctx {
     int wl_it0 = 0, wl_nit = 0;
     int wl_edge_lo = 0, wl_edge_hi = 0;
     int64_t wl_units = 0;
+    int wl_band = 0;                      // unit order of the cached list (row-major / band-major, epi_capi.cu build_worklist)
     // device-side timing of the dominant kernel (bench.py's roofline): events around every search launch
     static constexpr int kEvRing = 32;
     cudaEvent_t ev0[kEvRing] = {}, ev1[kEvRing] = {};
@@ -366,7 +367,7 @@ static int apply_folds(hpgv_epi_ctx *ctx, int F, const int32_t *fold_of_sample, 
     fl.tri = (allow_tri && tri_fits) ? 1 : 0;
     ctx->tri_suppressed = tri_fits && !allow_tri;
     ctx->npos = (int64_t) nb * bits_per_block;
-    fl.marg = 0; fl.marg_off = 0;
+    fl.marg = 0; fl.marg_off = 0; fl.marg_stride = 4; fl.mlist = 0;
     if (fl.tri) {
         fl.bw = 4;                                       // logical positions: word 3 of a block = its 4-bit tail
         fl.cb = nb; fl.nchunks = 1;
@@ -384,12 +385,16 @@ static int apply_folds(hpgv_epi_ctx *ctx, int F, const int32_t *fold_of_sample, 
         // single-block segments: the per-group marginals follow the planes of a chunk row when the staged packer (which
         // writes them) can run and a stage of 49 rows still fits 48 KB
         const char *old_packer = getenv("HPGV_PACK_WARP");
-        for (int with_marg = (fl.single && !(old_packer && old_packer[0] == '1')) ? 1 : 0; with_marg >= 0; with_marg--) {
-            fl.marg = with_marg;
+        const char *no_list = getenv("HPGV_MISS_LIST");          // A/B switch: "0" = marginals without the lists of missing samples
+        // level 2: quad + list of the group's missing samples, level 1: quad only, level 0: no marginals
+        for (int level = (fl.single && !(old_packer && old_packer[0] == '1')) ? ((no_list && no_list[0] == '0') ? 1 : 2) : 0; level >= 0; level--) {
+            fl.marg = level > 0;
+            fl.mlist = level == 2;
+            fl.marg_stride = level == 2 ? 4 + kMissListWords : 4;
             fl.marg_off = fl.cb * 3 * fl.bw;
-            fl.row_words = fl.cb * 3 * fl.bw + (with_marg ? fl.cb : 0);
+            fl.row_words = fl.cb * 3 * fl.bw + (level ? (fl.cb / 4) * fl.marg_stride : 0);
             if ((fl.row_words / 4) % 2 == 0) fl.row_words += 4;   // odd number of 16-byte groups per row: conflict-free LDS.128
-            if (!with_marg) break;
+            if (!level) break;
             if (pack_smem_map(ctx->npos, S, fl).total <= 96 * 1024 && (size_t) (kMaxWarps + kTileJ + 1) * fl.row_words * 4 <= 48 * 1024) break;
         }
     }
@@ -548,8 +553,11 @@ cudaError_t opt_in_smem(K kernel, size_t bytes) {
 }  // namespace
 
 static int build_worklist(hpgv_epi_ctx *ctx, int order, int ti, uint64_t first, uint64_t last) {
-    if (ctx->wl_nv == ctx->nv && ctx->wl_order == order && ctx->wl_ti == ti && ctx->wl_first == first && ctx->wl_last == last)
+    const char *bt_key = getenv("HPGV_BAND_TILES");
+    const int band_key = ((ctx->plane_words * sizeof(uint32_t)) > ((size_t) 64 << 20) ? 1 : 0) + (bt_key ? 2 * atoi(bt_key) : 0);
+    if (ctx->wl_nv == ctx->nv && ctx->wl_order == order && ctx->wl_ti == ti && ctx->wl_first == first && ctx->wl_last == last && ctx->wl_band == band_key)
         return HPGV_OK;
+    ctx->wl_band = band_key;
     const int64_t nv = ctx->nv;
     std::vector<int64_t> prefix;
     std::vector<int32_t> jt0;
@@ -591,14 +599,33 @@ static int build_worklist(hpgv_epi_ctx *ctx, int order, int ti, uint64_t first, 
         }
     }
     if (prefix.empty()) { prefix.push_back(0); jt0.push_back(0); }
-    // order 2: the tile origins of every unit, while the list stays small (8 bytes per unit of 512..640 pairs)
+    // order 2: the tile origins of every unit (8 bytes per unit of 512..640 pairs), while the list stays below 128 MB.
+    // When the packed planes do not fit the L2 (c3: 235 MB, c5: 391 MB against 126 MB) the units are listed band by band:
+    // a band is a range of j tiles whose rows -- all chunks of them -- take about a quarter of the L2, and every i tile
+    // works through the band before the next band is touched.  In row-major order every i tile streams ALL later rows
+    // from HBM again (c3: 366 GB per search measured, 1500 x the 245 MB of planes); band-major, a band is read once and
+    // the i rows once per band.
     std::vector<int2> desc;
     ctx->wl_has_desc = false;
-    if (order == 2 && units > 0 && units <= (int64_t) 2 << 20) {
+    if (order == 2 && units > 0 && units <= (int64_t) 16 << 20) {
         desc.reserve((size_t) units);
-        for (size_t t = 0; t < prefix.size(); t++) {
-            const int64_t n = (t + 1 < prefix.size() ? prefix[t + 1] : units) - prefix[t];
-            for (int64_t x = 0; x < n; x++) desc.push_back(make_int2((it0 + (int) t) * ti, (jt0[t] + (int) x) * kTileJ));
+        const size_t row_bytes_all = (size_t) ctx->fl.nchunks * ctx->fl.row_words * 4;
+        const size_t plane_bytes = ctx->plane_words * sizeof(uint32_t);
+        const char *bo = getenv("HPGV_BAND_ORDER");              // A/B switch: "0" keeps the row-major order
+        int64_t band_tiles = INT64_MAX;
+        if (plane_bytes > (size_t) 64 << 20 && !(bo && bo[0] == '0'))
+            band_tiles = std::max<int64_t>(1, (int64_t) (((size_t) 32 << 20) / (row_bytes_all * kTileJ)));
+        const char *bt = getenv("HPGV_BAND_TILES");              // tests: force a band width (in j tiles) whatever the plane size
+        if (bt && atoi(bt) > 0) band_tiles = atoi(bt);
+        const int64_t njt = (nv + kTileJ - 1) / kTileJ;
+        for (int64_t b0 = 0; b0 < njt; b0 += std::min<int64_t>(band_tiles, njt)) {
+            const int64_t b1 = band_tiles == INT64_MAX ? njt : std::min(njt, b0 + band_tiles);
+            for (size_t t = 0; t < prefix.size(); t++) {
+                const int64_t n = (t + 1 < prefix.size() ? prefix[t + 1] : units) - prefix[t];
+                const int64_t lo = std::max<int64_t>(jt0[t], b0), hi = std::min<int64_t>(jt0[t] + n, b1);
+                for (int64_t jt = lo; jt < hi; jt++) desc.push_back(make_int2((it0 + (int) t) * ti, (int) (jt * kTileJ)));
+            }
+            if (band_tiles == INT64_MAX) break;
         }
         CK(ctx->d_unit_desc.reserve(desc.size()));
         CK(cudaMemcpyAsync(ctx->d_unit_desc.p, desc.data(), desc.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));

@@ -173,6 +173,8 @@ __host__ __device__ __forceinline__ int64_t plane_word(const FoldLayout &fl, int
 // group_shift(q)/8; tail word m = k/2 keeps it in nibble 2*byte + (k&1), so that after a nibble-wise popcount n,
 // n & 0x0F0F0F0F adds to counter word 2m and (n >> 4) & 0x0F0F0F0F to counter word 2m + 1.
 __host__ __device__ constexpr uint32_t group_shift(int q) { return q == 0 ? 0u : (q == 1 ? 16u : (q == 2 ? 8u : 24u)); }
+// the same for a run-time block index: q = 0, 1, 2, 3 -> 0, 16, 8, 24
+__host__ __device__ __forceinline__ uint32_t group_shift_rt(uint32_t q) { return ((q & 1u) << 4) | ((q & 2u) << 2); }
 __host__ __device__ __forceinline__ int tri_word_off(int b, int g, int w) { return (b >> 2) * 36 + g * 12 + (b & 3) * 3 + w; }
 __host__ __device__ __forceinline__ int tri_tail_off(int nblocks, int b, int g) { return (nblocks >> 2) * 36 + (b >> 3) * 4 + g; }
 __host__ __device__ __forceinline__ int tri_tail_shift(int b) { return (int) (group_shift(b & 3) / 8 * 2 + ((b >> 2) & 1)) * 4; }

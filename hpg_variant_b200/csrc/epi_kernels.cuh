@@ -78,6 +78,10 @@ __global__ void pack_planes_kernel(const uint8_t *__restrict__ raw, int64_t nv, 
 struct PackSmem {
     size_t perm, ofs, row, out, total;
 };
+// list of a SNP's missing samples in one group of four blocks (FoldLayout::mlist), kMissListWords entries, 0 = end:
+//   [15:0] the missing samples among 16 consecutive bit positions   [20:16] left shift that puts them back in their word (0 or 16)
+//   [27:21] word offset of plane 0 of that word inside the group: block-in-group * 3 * slot words + word   [29:28] block in group
+constexpr int kMissListWords = 8;
 constexpr int kPackRows = 8;      // SNPs a CTA packs per iteration (their rows are contiguous on both sides)
 __host__ __device__ inline PackSmem pack_smem_map(int64_t npos, int64_t nsamples, const FoldLayout &fl) {
     PackSmem m;
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const uint8_t *__restric
     uint32_t *out_s = reinterpret_cast<uint32_t *>(psm + m.out);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int bw = flp->bw, lbw = bw == 8 ? 3 : 2, nwords = flp->nblocks * bw, tri = flp->tri, cb = flp->cb, nblocks = flp->nblocks;
-    const int row_words = flp->row_words, nchunks = flp->nchunks, marg = flp->marg, marg_off = flp->marg_off;
+    const int row_words = flp->row_words, nchunks = flp->nchunks, marg = flp->marg, marg_off = flp->marg_off, mstride = flp->marg_stride, mlist = flp->mlist;
     const int out_words = nchunks * row_words;                           // per SNP, chunk-major
     const int gstride = tri ? 12 : bw;                                   // words between the planes of one block
     const int bpt = flp->single ? 4 : 1;                                 // blocks per task (nblocks is a multiple of 4 then)
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const uint8_t *__restric
         int o;
         if (tri) o = w < 3 ? tri_word_off(b, 0, w) : -((tri_tail_off(nblocks, b, 0) + 1) | (tri_tail_shift(b) << 24));
         else o = (b / cb) * row_words + ((b % cb) * 3) * bw + w;
-        const int mq = tri ? marg_off + (b >> 2) * 4 : (b / cb) * row_words + marg_off + ((b % cb) >> 2) * 4;
+        const int mq = tri ? marg_off + (b >> 2) * 4 : (b / cb) * row_words + marg_off + ((b % cb) >> 2) * mstride;
         ofs_s[wb] = make_int2(o, mq | ((int) group_shift(b & 3) << 24) | ((tri && w == 3) ? (1 << 30) : 0));
     }
     for (int64_t snp0 = (int64_t) blockIdx.x * kPackRows; snp0 < nv; snp0 += (int64_t) gridDim.x * kPackRows) {
@@ -139,8 +143,8 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const uint8_t *__restric
             const int r = task / tasks_per_row, tg = task - r * tasks_per_row;
             uint32_t *dst = out_s + r * out_words;
             const uint8_t *row = row_s + mis + (size_t) r * nsamples;
-            uint32_t nacc = 0, missacc = 0, tailacc = 0;
-            int tail_o = 0, mq = 0;
+            uint32_t nacc = 0, missacc = 0, tailacc = 0, my_ent = 0;     // my_ent: lane e keeps entry e of the group's missing list
+            int tail_o = 0, mq = 0, nent = 0;
             for (int q = 0; q < bpt; q++) {
                 const int b = tg * bpt + q;
                 uint32_t n = 0, inno_any = 0;
@@ -151,7 +155,19 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const uint8_t *__restric
                     const uint32_t m0 = __ballot_sync(0xffffffffu, g == 0);
                     const uint32_t m1 = __ballot_sync(0xffffffffu, g == 1);
                     const uint32_t m2 = __ballot_sync(0xffffffffu, g == 2);
-                    if (marg) inno_any |= __ballot_sync(0xffffffffu, col >= 0 && g > 2u);      // samples that are in no plane
+                    if (marg) {
+                        const uint32_t inno = __ballot_sync(0xffffffffu, col >= 0 && g > 2u);      // samples that are in no plane
+                        inno_any |= inno;
+                        if (mlist && inno) {
+#pragma unroll
+                            for (int half = 0; half < 2; half++) {
+                                const uint32_t m16 = (inno >> (16 * half)) & 0xffffu;
+                                if (!m16) continue;
+                                if (lane == nent) my_ent = m16 | ((uint32_t) (16 * half) << 16) | ((uint32_t) (q * 3 * bw + w) << 21) | ((uint32_t) q << 28);
+                                nent++;
+                            }
+                        }
+                    }
                     uint32_t mine = lane == 0 ? m0 : (lane == 1 ? m1 : m2);
                     const int2 om = ofs_s[wb];
                     mq = om.y & 0xFFFFFF;
@@ -167,12 +183,15 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const uint8_t *__restric
                 nacc += n << group_shift(q);                        // bpt == 4 whenever marg is set: q = b & 3
                 if (inno_any) missacc |= 0xFFu << group_shift(q);
             }
+            // with a list that holds every missing sample of the group no block needs its genotype-2 cells counted directly
+            const bool listed = mlist && nent <= kMissListWords;
             if (lane < 3) {
                 if (tailacc) atomicOr(dst + tail_o + lane, tailacc);     // the tail word is shared with the neighbouring group
                 if (marg) dst[mq + lane] = nacc;
             } else if (lane == 3 && marg) {
-                dst[mq + 3] = missacc;
+                dst[mq + 3] = listed ? 0u : missacc;
             }
+            if (mlist && lane < kMissListWords) dst[mq + 4 + lane] = (listed && lane < nent) ? my_ent : 0u;
         }
         __syncthreads();
         // chunk ch of the nr SNPs is one contiguous run of nr * row_words words in global memory
@@ -867,11 +886,12 @@ __device__ __forceinline__ void single_block2(const uint32_t *irow, const uint32
 }
 // In a block where SNP i has no missing sample every sample has one of i's three genotypes:
 // n(2, gb) = N_gb(j) - n(0, gb) - n(1, gb), byte by byte (the bytes never borrow: N_gb >= n(0, gb) + n(1, gb) in every block)
-__device__ __forceinline__ void derive_row2(uint32_t imiss, const uint4 nj, uint32_t (&pk)[9]) {
-    const uint32_t njv[3] = {nj.x, nj.y, nj.z};
+// corr[gb]: the samples SNP i is missing that have genotype gb of SNP j (they are in no cell), from the group's list
+__device__ __forceinline__ void derive_row2(uint32_t imiss, const uint4 nj, uint32_t (&pk)[9], uint32_t c0 = 0, uint32_t c1 = 0, uint32_t c2 = 0) {
+    const uint32_t njv[3] = {nj.x, nj.y, nj.z}, corr[3] = {c0, c1, c2};
 #pragma unroll
     for (int gb = 0; gb < 3; gb++) {
-        const uint32_t derived = njv[gb] - pk[gb] - pk[3 + gb];
+        const uint32_t derived = njv[gb] - pk[gb] - pk[3 + gb] - corr[gb];
         pk[6 + gb] = (derived & ~imiss) | (pk[6 + gb] & imiss);
     }
 }
@@ -1240,16 +1260,33 @@ __global__ void __launch_bounds__((SINGLE ? kTriWarps : kMaxWarps) * 32, 1) sear
                 const int off = (b4 - b_lo) * 3 * SW;
                 uint32_t imiss = 0xFFFFFFFFu;                                   // without marginals every block is counted
                 uint4 nj = make_uint4(0u, 0u, 0u, 0u);
+                uint32_t c0 = 0, c1 = 0, c2 = 0;
                 if (ctl->fl.marg && a.tri_derive) {
-                    const int mq = ctl->fl.marg_off + (b4 - b_lo);              // one quad per four blocks
+                    const int mq = ctl->fl.marg_off + ((b4 - b_lo) >> 2) * ctl->fl.marg_stride;   // one quad (+ list) per four blocks
                     imiss = irow[mq + 3];
                     nj = *reinterpret_cast<const uint4 *>(jrow + mq);
+                    if (ctl->fl.mlist) {
+                        // SNP i's missing samples of this group, 16 bit positions per entry (warp-uniform): which genotype of SNP j
+                        // do they have?  Those samples are in no cell, and the derivation below would put them into row 2.
+                        const uint32_t *il = irow + mq + 4;
+#pragma unroll 1
+                        for (int e = 0; e < kMissListWords; e++) {
+                            const uint32_t ent = il[e];
+                            if (ent == 0) break;
+                            const uint32_t m = (ent & 0xffffu) << ((ent >> 16) & 31u);
+                            const uint32_t *jp = jrow + off + ((ent >> 21) & 127u);
+                            const uint32_t unit = 1u << group_shift_rt(ent >> 28);
+                            c0 += (uint32_t) __popc(jp[0] & m) * unit;
+                            c1 += (uint32_t) __popc(jp[SW] & m) * unit;
+                            c2 += (uint32_t) __popc(jp[2 * SW] & m) * unit;
+                        }
+                    }
                 }
                 single_block2<BW, 0>(irow + off, jrow + off, imiss, pk);
                 single_block2<BW, 1>(irow + off, jrow + off, imiss, pk);
                 single_block2<BW, 2>(irow + off, jrow + off, imiss, pk);
                 single_block2<BW, 3>(irow + off, jrow + off, imiss, pk);
-                derive_row2(imiss, nj, pk);
+                derive_row2(imiss, nj, pk, c0, c1, c2);
                 const int k = b4 >> 2;
 #pragma unroll
                 for (int c = 0; c < 9; c++) cnts[k * 9 + c] = pk[c];

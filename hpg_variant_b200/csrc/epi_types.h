@@ -46,6 +46,12 @@ struct FoldLayout {
                            // per-block genotype counts as packed byte counters and 0xFF in the byte of every block where the
                            // SNP has a sample in no plane (tri layout: always; single-block layouts: when the staged packer runs)
     int marg_off;          // word offset of the first quad inside a chunk row
+    int marg_stride;       // words per group of four blocks in the marginal area: 4 (the quad), or 4 + kMissListWords when
+    int mlist;             // the quad is followed by the group's list of the SNP's missing samples (single-block layouts
+                           // other than tri): entries of 16 sample bits each, see kMissListWords in epi_kernels.cuh.  The
+                           // search then derives genotype 2 of SNP i in EVERY block and takes the listed samples out of the
+                           // derived cells one entry at a time; `missing` (word 3 of the quad) only marks the blocks of a
+                           // group whose list overflowed, which are counted directly as before
     int nblocks;           // real blocks along the sample axis (single: nseg rounded up to a multiple of 4)
     int cb;                // blocks per chunk (single: multiple of 4)
     int nchunks;

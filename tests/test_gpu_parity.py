@@ -230,11 +230,13 @@ def test_histogram_thresholds_do_not_change_results(engine, monkeypatch, nv, A, 
     assert np.array_equal(ev["conf"][:, 0], with_hist["conf"][0, :8])
 
 
-@pytest.mark.parametrize("switch", ["HPGV_UNIT_DESC=0", "HPGV_TRI_DERIVE=0", "HPGV_TRI_WARPS=16", "HPGV_STAGES=2", "HPGV_STAGGER=0", "HPGV_PACK_WARP=1", "HPGV_LIST_SCAN=0"])
+@pytest.mark.parametrize("switch", ["HPGV_UNIT_DESC=0", "HPGV_TRI_DERIVE=0", "HPGV_TRI_WARPS=16", "HPGV_STAGES=2", "HPGV_STAGGER=0", "HPGV_PACK_WARP=1", "HPGV_LIST_SCAN=0",
+                                    "HPGV_MISS_LIST=0", "HPGV_FIRST_WAIT=0", "HPGV_FRESH_BOUND=1", "HPGV_BAND_TILES=5"])
 def test_development_switches_do_not_change_results(engine, monkeypatch, switch):
     """Every A/B switch of the library selects another route to the same bytes (prefix-table walk instead of the per-unit
     descriptors, every cell counted directly, 16 warps, two stages, no stagger, the one-warp-per-word packer, heap-ordered
-    instead of array lists)."""
+    instead of array lists, marginals without the lists of missing samples, no wait for the first units' histogram counts,
+    other CTAs' bounds adopted every unit, units listed band by band -- the order of data sets larger than the L2)."""
     nv, A, F, rank = 1200, 2000, 10, 40           # c3-shaped samples: 8-word single-block layout with marginals
     g = synth.make_dataset(nv, A, A, seed=99, missing=0.01, planted=2)
     fos, _ = h.k_folds(A, A, F, seed=3)
