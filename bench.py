@@ -452,18 +452,21 @@ class Runner:
 
         # ---- e2e: host buffers in, host result out ----
         if e2e:
+            # N = 1: the C-ABI call hpgv_epi_run_host (host pointers in and out).  N > 1: ShardedSearch.run_from_host -- every
+            # rank uploads 1/N of the SNP rows from its pinned host copy, the slices are all-gathered over NVLink, then
+            # pack + search + all-gather of the lists + merge, and the final ranking comes back to the host of every rank.
+            def e2e_step():
+                if world == 1:
+                    eng.run_host(g, A, U, F, fos, order, h.SUBSET_TRAINING, RANK_SIZE, first, last, out=h_out)
+                else:
+                    shard.run_from_host(g_pinned, A, U, F, fos, order, h.SUBSET_TRAINING, total)
             for _ in range(2):
-                eng.run_host(g, A, U, F, fos, order, h.SUBSET_TRAINING, RANK_SIZE, first, last, out=h_out)
+                e2e_step()
             self.barrier()
             e2e_steps = max(3, min(steps, 10))
             t0 = time.perf_counter()
             for _ in range(e2e_steps):
-                eng.run_host(g, A, U, F, fos, order, h.SUBSET_TRAINING, RANK_SIZE, first, last, out=h_out)
-                if world > 1:
-                    d_local.copy_(torch.from_numpy(h_out.view(np.uint8).reshape(-1)), non_blocking=False)
-                    dist.all_gather_into_tensor(d_all, d_local)
-                    eng.merge_device(order, h.SUBSET_TRAINING, world, RANK_SIZE, d_all.data_ptr(), d_final.data_ptr())
-                    d_final.cpu()
+                e2e_step()
             self.barrier()
             e2e_s = self.reduce([time.perf_counter() - t0], "MAX")[0]
             out["e2e_value"] = total * F * e2e_steps / e2e_s
@@ -616,7 +619,9 @@ def main():
                        "sharding": f"{world} contiguous combination-index ranges", "l2": "flushed between timed steps (256 MiB write)",
                        "layout": lay},
             "clocks": r["clocks"],
-            "e2e": {"value": r["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": int(nv * S + lay["num_blocks"] * (4 if lay["block_words"] == 3 else lay["block_words"]) * 32 * 4),
+            "e2e": {"value": r["e2e_value"], "unit": UNIT,
+                    "h2d_bytes_per_step": int(-(-nv // world) * S + lay["num_blocks"] * (4 if lay["block_words"] == 3 else lay["block_words"]) * 32 * 4),
+                    "h2d_note": "per rank: its 1/N slice of the genotype rows (all-gathered over NVLink when N > 1) + the fold permutation",
                     "d2h_bytes_per_step": F * RANK_SIZE * 40, "steps": r["e2e_steps"],
                     "first_call_s": r["first_call_s"],
                     "first_call_note": "first pack+search of this shape, once per run: builds and uploads the work list (unit descriptors), sizes the buffers; later calls reuse them"},

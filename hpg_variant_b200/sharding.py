@@ -71,6 +71,29 @@ class ShardedSearch:
         self.eng.merge_device(order, eval_subset, self.world, self.N, self.d_all.data_ptr(), self.d_final.data_ptr())
         return self.d_final
 
+    def run_from_host(self, g_pinned, num_affected, num_unaffected, num_folds, fold_of_sample, order, eval_subset, total):
+        """The whole path from HOST buffers: g_pinned is the pinned uint8 tensor [num_variants, A + U] every rank holds.
+        Each rank uploads only its 1/world slice of the SNP rows over its own PCIe link and the slices are all-gathered
+        over NVLink (every rank needs every SNP: a pair joins two arbitrary rows), then pack, search, gather, merge.
+        Returns the final ranking as a host array (identical on every rank)."""
+        import torch
+        nv, S = g_pinned.shape
+        per = -(-nv // self.world)
+        if getattr(self, "_raw_shape", None) != (nv, S):
+            self.d_raw_full = torch.empty((self.world * per, S), dtype=torch.uint8, device=self.d_local.device)
+            self.d_raw_slice = torch.empty((per, S), dtype=torch.uint8, device=self.d_local.device)
+            self._raw_shape = (nv, S)
+        lo, hi = min(nv, self.rank * per), min(nv, (self.rank + 1) * per)
+        if self.world == 1:
+            self.d_raw_full[:nv].copy_(g_pinned, non_blocking=True)
+        else:
+            self.d_raw_slice[: hi - lo].copy_(g_pinned[lo:hi], non_blocking=True)
+            self.dist.all_gather_into_tensor(self.d_raw_full.view(-1), self.d_raw_slice.view(-1))
+        self.eng.load_dataset_device(self.d_raw_full.data_ptr(), nv, num_affected, num_unaffected)
+        self.eng.set_folds(num_folds, fold_of_sample)
+        self.run(order, eval_subset, total)
+        return self.result()
+
     def result(self):
         """Host copy of the final ranking as a structured array [F, N]."""
         return self.d_final.cpu().numpy().view(MODEL_DTYPE).reshape(self.F, self.N)

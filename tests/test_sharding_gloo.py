@@ -106,3 +106,82 @@ def test_two_rank_gather_and_merge_equals_full_search(oracle, order, nv, A, U, F
     assert np.array_equal(merged["risky_mask"], full["risky_mask"])
     assert np.array_equal(merged["conf"], full["conf"])
     assert np.array_equal(merged["accuracy"], full["ba"], equal_nan=True)
+
+
+class _CpuEngine:
+    """Stand-in for EpistasisEngine in the gloo test of ShardedSearch.run_from_host: same calls, the oracle does the search
+    and a numpy merge does the merge, on the CPU buffers whose addresses it is handed (test infrastructure only)."""
+
+    def __init__(self, oracle, F, N):
+        self.oracle, self.F, self.N = oracle, F, N
+        self.seen = None
+
+    @staticmethod
+    def _view(ptr, nbytes):
+        import ctypes
+        return np.ctypeslib.as_array((ctypes.c_uint8 * nbytes).from_address(ptr))
+
+    def load_dataset_device(self, ptr, nv, A, U):
+        self.g = self._view(ptr, nv * (A + U)).reshape(nv, A + U).copy()
+        self.A, self.U = A, U
+
+    def set_folds(self, F, fos):
+        self.fos = np.asarray(fos, np.int32)
+
+    def search_device(self, order, subset, N, first, last, out_ptr):
+        self.order = order
+        part, _ = self.oracle.search(self.g, self.A, self.U, order, self.fos, subset, N, first=first, last=last, threads=1, num_folds=self.F)
+        self._view(out_ptr, part.nbytes)[:] = part.view(np.uint8).reshape(-1)
+
+    def merge_device(self, order, subset, world, N, lists_ptr, out_ptr):
+        lists = self._view(lists_ptr, world * self.F * N * 40).view(MODEL_DTYPE).reshape(world, self.F, N)
+        self._view(out_ptr, self.F * N * 40)[:] = canonical_merge(lists, N).view(np.uint8).reshape(-1)
+
+
+def _worker_from_host(rank, world, port, nv, A, U, F, rank_size, q):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    import torch
+    import torch.distributed as dist
+    import oracle_lib
+    from hpg_variant_b200 import sharding as sh, synth
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        oracle = oracle_lib.Checker("oracle")
+        g = synth.make_dataset(nv, A, U, seed=77, missing=0.01, planted=1)
+        fos = (np.concatenate([np.arange(A), np.arange(U)]) % F).astype(np.int32)
+        eng = _CpuEngine(oracle, F, rank_size)
+        shard = sh.ShardedSearch(eng, dist, rank, world, F, rank_size, "cpu")
+        total = int(oracle._fn("num_combinations")(nv, 2))
+        res = shard.run_from_host(torch.from_numpy(g), A, U, F, fos, 2, 1, total)
+        assert np.array_equal(eng.g, g)           # the all-gathered slices are the whole matrix, on every rank
+        q.put((rank, res.tobytes()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_run_from_host_uploads_slices_and_gathers(oracle):
+    """ShardedSearch.run_from_host: every rank contributes 1/world of the SNP rows (41 rows over 2 ranks: uneven), the
+    all-gather rebuilds the matrix, and the final ranking equals the full search on both ranks."""
+    import torch.multiprocessing as mp
+    from hpg_variant_b200 import synth
+    nv, A, U, F, rank_size, world, port = 41, 60, 70, 4, 10, 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_from_host, args=(r, world, port, nv, A, U, F, rank_size, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0][1] == got[1][1]
+    g = synth.make_dataset(nv, A, U, seed=77, missing=0.01, planted=1)
+    fos = (np.concatenate([np.arange(A), np.arange(U)]) % F).astype(np.int32)
+    full, _ = oracle.search(g, A, U, 2, fos, 1, rank_size, threads=2, num_folds=F)
+    merged = np.frombuffer(got[0][1], MODEL_DTYPE).reshape(F, rank_size)
+    assert np.array_equal(merged["snp"][..., :2], full["snp"][..., :2]) and np.array_equal(merged["conf"], full["conf"])
+    assert np.array_equal(merged["accuracy"], full["ba"], equal_nan=True)
