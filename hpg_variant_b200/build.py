@@ -16,8 +16,10 @@ CLI = os.path.join(HERE, "hpg-var-gwas-b200")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "-ccbin", "g++",
+    "-Xcompiler", "-fPIC", "-ccbin", "g++",
 ]
+# one translation unit per kernel family (compiled in parallel: the search kernels dominate the build) + the C-ABI
+CUDA_UNITS = ["epi_capi.cu", "epi_k_search2.cu", "epi_k_search3.cu", "epi_k_search3v2.cu", "epi_k_search3v3.cu"]
 
 
 def _newer(target, sources):
@@ -39,10 +41,27 @@ def build(force=False, verbose=False):
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
     inc = [os.path.join(os.path.dirname(HERE), "include", "hpgv_epi.h")]
     if force or _newer(LIB, srcs + inc):
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "epi_capi.cu")]
-        if verbose:
-            print(" ".join(cmd), file=sys.stderr)
-        subprocess.run(cmd, check=True, env=_env())
+        from concurrent.futures import ThreadPoolExecutor
+        objdir = os.path.join(HERE, "build")
+        os.makedirs(objdir, exist_ok=True)
+
+        def compile_unit(name):
+            obj = os.path.join(objdir, name[:-3] + ".o")
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, name)]
+            if verbose:
+                print(" ".join(cmd), file=sys.stderr)
+            r = subprocess.run(cmd, env=_env(), capture_output=True, text=True)
+            return name, obj, r
+
+        with ThreadPoolExecutor(max_workers=len(CUDA_UNITS)) as pool:
+            results = list(pool.map(compile_unit, CUDA_UNITS))
+        for name, obj, r in results:
+            if verbose or r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+            if r.returncode != 0:
+                raise subprocess.CalledProcessError(r.returncode, "nvcc " + name)
+        subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "g++", "-o", LIB] + [obj for _, obj, _ in results],
+                       check=True, env=_env())
     host_src = os.path.join(CSRC, "epi_host.cpp")
     if os.path.exists(host_src):
         compat = os.path.join(os.path.dirname(HERE), "include", "hpgv_epi_compat.h")

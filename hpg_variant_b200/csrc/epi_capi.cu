@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "epi_kernels.cuh"
+#include "epi_launch.h"
 
 using namespace hpgv;
 
@@ -102,6 +103,7 @@ struct hpgv_epi_ctx {
     // search3v2_kernel: per-SNP lists of missing samples (made on the first order-3 search after set_folds)
     DevBuf<uint32_t> d_miss;
     DevBuf<int> d_miss_max;
+    DevBuf<uint32_t> d_vmask;             // search3v3_kernel: bit positions of every block that hold a sample
     bool miss_valid = false;
     int miss_cap = 0;
     DevBuf<hpgv_epi_model_t> d_out;
@@ -197,7 +199,7 @@ extern "C" void hpgv_epi_destroy(hpgv_epi_ctx *ctx) {
     cudaSetDevice(ctx->device);
     ctx->raw_owned.release(); ctx->d_fl.release(); ctx->d_perm.release(); ctx->d_blk.release(); ctx->d_planes.release();
     ctx->d_lists.release(); ctx->d_list_cnt.release(); ctx->d_gthr.release(); ctx->d_hist.release(); ctx->d_hmax.release(); ctx->d_dbg.release();
-    ctx->d_prefix.release(); ctx->d_jt0.release(); ctx->d_unit_desc.release(); ctx->d_out.release(); ctx->d_merge_in.release(); ctx->d_miss.release(); ctx->d_miss_max.release();
+    ctx->d_prefix.release(); ctx->d_jt0.release(); ctx->d_unit_desc.release(); ctx->d_out.release(); ctx->d_merge_in.release(); ctx->d_miss.release(); ctx->d_miss_max.release(); ctx->d_vmask.release();
     for (int k = 0; k < hpgv_epi_ctx::kEvRing; k++) { if (ctx->ev0[k]) cudaEventDestroy(ctx->ev0[k]); if (ctx->ev1[k]) cudaEventDestroy(ctx->ev1[k]); }
     if (ctx->ev_stage) cudaEventDestroy(ctx->ev_stage);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -675,8 +677,7 @@ static SearchShape pick_shape(const hpgv_epi_ctx *ctx, int order, int rank) {
     return best;
 }
 
-template <typename K>
-static int launch_search(hpgv_epi_ctx *ctx, K kernel, const SearchShape &shape, SearchArgs &args, int F, int rank) {
+static int launch_search(hpgv_epi_ctx *ctx, search_kernel_t kernel, const SearchShape &shape, SearchArgs &args, int F, int rank) {
     CK(opt_in_smem(kernel, shape.smem));
     int64_t grid = ctx->num_sms;                       // one persistent CTA per SM
     grid = std::max<int64_t>(1, std::min<int64_t>(grid, std::max<int64_t>(args.num_units, 1)));
@@ -787,6 +788,37 @@ static int build_miss_lists(hpgv_epi_ctx *ctx) {
     return mcap;
 }
 
+// search3v3_kernel (balanced cohorts, pre-filter applicable): eight warps, the pair table in registers
+static Shape3 pick_shape3b(const hpgv_epi_ctx *ctx, int rank, int mcap) {
+    const FoldLayout &fl = ctx->fl;
+    Shape3 best;
+    const int nwc = fl.single ? fl.nblocks / 4 : fl.F;
+    if (fl.tri || fl.nchunks > 15 || fl.cb * 3 * fl.bw > 2047 || fl.nblocks / 4 > 1023 || nwc > 5) return best;   // (built for <= 5 counter words per cell)
+    for (int in_smem = 1; in_smem >= 0; in_smem--) {
+        if (in_smem && (size_t) fl.F * rank * sizeof(Cand) > 24 * 1024) continue;
+        for (int ni = 4; ni >= 1; ni >>= 1) {
+            const Smem3bMap m = search3v3_smem_map(fl, 8, ni, mcap, rank, in_smem != 0);
+            if (m.total <= (size_t) ctx->max_smem_optin) {
+                best.tj = 8; best.ni = ni; best.lists_in_smem = in_smem != 0; best.smem = m.total;
+                return best;
+            }
+        }
+    }
+    return best;
+}
+
+// valid-sample masks per block word (which bit positions hold a sample), for the 1' plane of search3v3_kernel
+static int build_vmask(hpgv_epi_ctx *ctx) {
+    const int bw = ctx->fl.bw, nwords = ctx->fl.nblocks * bw;
+    std::vector<uint32_t> vm((size_t) nwords, 0u);
+    for (int64_t pos = 0; pos < ctx->npos; pos++)
+        if (ctx->perm[(size_t) pos] >= 0) vm[(size_t) (pos >> 5)] |= 1u << (pos & 31);
+    CK(ctx->d_vmask.reserve(vm.size()));
+    CK(cudaMemcpyAsync(ctx->d_vmask.p, vm.data(), vm.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HPGV_OK;
+}
+
 // units of search3v2_kernel: (j tile, k tile) pairs that hold some j < k, longest i loops first
 static int build_worklist3(hpgv_epi_ctx *ctx, int tj, uint64_t first, uint64_t last) {
     if (ctx->wl_nv == ctx->nv && ctx->wl_order == 3 && ctx->wl_ti == -tj && ctx->wl_first == first && ctx->wl_last == last) return HPGV_OK;
@@ -861,14 +893,32 @@ static int do_search(hpgv_epi_ctx *ctx, int order, int eval_subset, int rank, ui
     }
 
     // order 3: the kernel with resident (j, k) tiles when its tables fit shared memory and no SNP misses hundreds of samples
-    bool use_v2 = false;
+    bool use_v2 = false, use_v3 = false;
     SearchShape shape;
+    const bool balanced = fl.balanced && fl.A <= 65535;
+    args.eval_fn = ctx->eval_fn == kEvalCA ? kEvalBA : ctx->eval_fn;      // the reference turns code 0 into BA (model.c:465-467)
+    // the balanced pre-filter (epilogue_balanced_t) orders by TP - FP: BA on the TRAINING part of equal folds only
+    args.prefilter = (balanced && fl.eqfolds && args.training && args.eval_fn == kEvalBA) ? 1 : 0;
     if (order == 3) {
-        const char *v2 = getenv("HPGV_SEARCH3_V2");           // A/B switch: "0" keeps the plain order-3 kernel
+        const char *v2 = getenv("HPGV_SEARCH3_V2");           // A/B switches: "0" keeps the plain order-3 kernel,
+        const char *v3 = getenv("HPGV_SEARCH3_V3");           // "1" runs the one-thread-per-triple kernel where it applies (measured slower)
         if (!(v2 && v2[0] == '0')) {
             const int mcap = build_miss_lists(ctx);
             if (mcap < 0) return mcap;
-            const Shape3 s3 = mcap > 0 ? pick_shape3(ctx, rank, mcap) : Shape3();
+            // one thread per triple, pair table in registers: balanced cohorts whose pre-filter applies (its two-pass epilogue
+            // only pays when nearly every fold stops at the pre-filter).  Opt-in: 18 % fewer instructions than the
+            // two-threads-per-triple kernel but eight warps per SM instead of 12-16, and slower for it (c4: 12.3 s against 11.4 s)
+            const Shape3 s3b = (mcap > 0 && args.prefilter && v3 && v3[0] == '1') ? pick_shape3b(ctx, rank, mcap) : Shape3();
+            if (s3b.tj > 0) {
+                int rc3 = build_worklist3(ctx, s3b.tj, first, last);
+                if (rc3 == HPGV_OK) rc3 = build_vmask(ctx);
+                if (rc3 == HPGV_OK) {
+                    use_v3 = true;
+                    shape.nthreads = s3b.tj * 32; shape.lists_in_smem = s3b.lists_in_smem; shape.nstages = 2; shape.smem = s3b.smem;
+                    args.v2_ni = s3b.ni; args.v2_mcap = mcap; args.v2_miss = ctx->d_miss.p; args.v3_vmask = ctx->d_vmask.p;
+                } else if (rc3 != HPGV_E_UNSUPPORTED) return rc3;
+            }
+            const Shape3 s3 = (mcap > 0 && !use_v3) ? pick_shape3(ctx, rank, mcap) : Shape3();
             if (s3.tj > 0) {
                 int rc3 = build_worklist3(ctx, s3.tj, first, last);
                 if (rc3 == HPGV_OK) {
@@ -879,10 +929,10 @@ static int do_search(hpgv_epi_ctx *ctx, int order, int eval_subset, int rank, ui
             }
         }
     }
-    if (!use_v2) shape = pick_shape(ctx, order, rank);
+    if (!use_v2 && !use_v3) shape = pick_shape(ctx, order, rank);
     if (shape.nthreads == 0)
         FAIL(HPGV_E_UNSUPPORTED, "fold count x cell count does not fit the shared memory of an SM (" + std::to_string(ctx->max_smem_optin) + " bytes)");
-    int rc = use_v2 ? HPGV_OK : build_worklist(ctx, order, shape.nthreads / 32, first, last);
+    int rc = (use_v2 || use_v3) ? HPGV_OK : build_worklist(ctx, order, shape.nthreads / 32, first, last);
     if (rc) return rc;
     args.unit_prefix = ctx->d_prefix.p;
     args.unit_jt0 = ctx->d_jt0.p;
@@ -896,37 +946,20 @@ static int do_search(hpgv_epi_ctx *ctx, int order, int eval_subset, int rank, ui
     args.edge_lo = ctx->wl_edge_lo;
     args.edge_hi = ctx->wl_edge_hi;
 
-    // the packed-pair epilogue needs A == U (r = 1: the float32 rule is exact) and 16-bit class sizes
-    const bool balanced = fl.balanced && fl.A <= 65535;
-    args.eval_fn = ctx->eval_fn == kEvalCA ? kEvalBA : ctx->eval_fn;      // the reference turns code 0 into BA (model.c:465-467)
+    // (balanced: the packed-pair epilogue needs A == U -- r = 1: the float32 rule is exact -- and 16-bit class sizes)
     {
-        // the balanced pre-filter (epilogue_balanced_t) orders by TP - FP: BA on the TRAINING part of equal folds only
-        args.prefilter = (balanced && fl.eqfolds && args.training && args.eval_fn == kEvalBA) ? 1 : 0;
         // score histogram: the pre-filter's conditions and the order-2 kernel's step modes
         const char *hs = getenv("HPGV_HIST");
         args.use_hist = (order == 2 && args.prefilter && !(hs && hs[0] == '0')) ? 1 : 0;
         args.hist_bins = fl.A + 1;
     }
-    int grid = 0;
-#define HPGV_LAUNCH(KERNEL)                                                                          \
-    do {                                                                                             \
-        if (fl.bw == 4) grid = balanced ? launch_search(ctx, KERNEL<4, true, true>, shape, args, F, rank)    \
-                                        : launch_search(ctx, KERNEL<4, true, false>, shape, args, F, rank);  \
-        else if (fl.w7 && fl.single) grid = balanced ? launch_search(ctx, KERNEL<7, true, true>, shape, args, F, rank)    \
-                                                     : launch_search(ctx, KERNEL<7, true, false>, shape, args, F, rank);  \
-        else if (fl.w7) grid = balanced ? launch_search(ctx, KERNEL<7, false, true>, shape, args, F, rank)      \
-                                        : launch_search(ctx, KERNEL<7, false, false>, shape, args, F, rank);    \
-        else if (fl.single) grid = balanced ? launch_search(ctx, KERNEL<8, true, true>, shape, args, F, rank)    \
-                                            : launch_search(ctx, KERNEL<8, true, false>, shape, args, F, rank);  \
-        else grid = balanced ? launch_search(ctx, KERNEL<8, false, true>, shape, args, F, rank)      \
-                             : launch_search(ctx, KERNEL<8, false, false>, shape, args, F, rank);    \
-    } while (0)
-    if (order == 2 && fl.tri) grid = balanced ? launch_search(ctx, search2_kernel<3, true, true>, shape, args, F, rank)
-                                              : launch_search(ctx, search2_kernel<3, true, false>, shape, args, F, rank);
-    else if (order == 2) HPGV_LAUNCH(search2_kernel);
-    else if (use_v2) HPGV_LAUNCH(search3v2_kernel);
-    else HPGV_LAUNCH(search3_kernel);
-#undef HPGV_LAUNCH
+    // the kernel variant of this layout (instantiated in epi_k_*.cu, one translation unit per kernel family)
+    const int bwcode = (order == 2 && fl.tri) ? 3 : (fl.bw == 4 ? 4 : (fl.w7 ? 7 : 8));
+    search_kernel_t kernel = order == 2 ? kernel_search2(bwcode, fl.single != 0, balanced)
+                             : (use_v3 ? kernel_search3v3(bwcode, fl.single != 0)
+                                       : (use_v2 ? kernel_search3v2(bwcode, fl.single != 0, balanced) : kernel_search3(bwcode, fl.single != 0, balanced)));
+    if (!kernel) FAIL(HPGV_E_UNSUPPORTED, "no search kernel was built for this sample layout");
+    const int grid = launch_search(ctx, kernel, shape, args, F, rank);
     if (grid < 0) return grid;
 
     MergeArgs m{};

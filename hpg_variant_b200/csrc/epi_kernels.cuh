@@ -1,4 +1,6 @@
 // epi_kernels.cuh -- CUDA kernels of the epistasis engine (sm_100a).
+// (Included by epi_capi.cu and by one epi_k_*.cu per search-kernel family, which build.py compiles in parallel: everything
+// that is not a template has internal linkage.)
 //
 //   pack_rows_kernel     bytes -> (fold, class)-segmented bit planes, staged through shared memory, with the per-block
 //                        marginals and missing masks of the byte-counter layouts  (replaces set_genotypes_masks + get_k_folds_masks)
@@ -42,7 +44,7 @@ namespace hpgv {
 // One warp per (snp, block, word): lane l reads the genotype byte of the sample
 // mapped to bit l and three ballots produce the three plane words.
 // perm[pos] = dataset column of the sample at bit position pos, or -1 (padding).
-__global__ void pack_planes_kernel(const uint8_t *__restrict__ raw, int64_t nv, int64_t nsamples,
+static __global__ void pack_planes_kernel(const uint8_t *__restrict__ raw, int64_t nv, int64_t nsamples,
                                    const int32_t *__restrict__ perm, const FoldLayout *__restrict__ flp, int64_t snp_pad,
                                    uint32_t *__restrict__ planes) {
     const FoldLayout &fl = *flp;
@@ -92,7 +94,7 @@ __host__ __device__ inline PackSmem pack_smem_map(int64_t npos, int64_t nsamples
     m.total = m.out + (size_t) kPackRows * fl.nchunks * fl.row_words * 4;
     return m;
 }
-__global__ void __launch_bounds__(256) pack_rows_kernel(const uint8_t *__restrict__ raw, int64_t nv, int64_t nsamples,
+static __global__ void __launch_bounds__(256) pack_rows_kernel(const uint8_t *__restrict__ raw, int64_t nv, int64_t nsamples,
                                                         const int32_t *__restrict__ perm, const FoldLayout *__restrict__ flp,
                                                         int64_t snp_pad, int64_t npos, uint32_t *__restrict__ planes) {
     extern __shared__ __align__(16) uint8_t psm[];
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const uint8_t *__restric
 // The samples every SNP is missing (in no plane although the bit position holds a sample), as a list of at most mcap - 1
 // entries per SNP followed by kMissEnd (see search3v2_kernel for the entry format); rows past the last SNP get empty lists.
 // One warp per SNP.  miss == nullptr: only the longest list's length is computed (max_cnt).
-__global__ void miss_list_kernel(const uint8_t *__restrict__ raw, int64_t nv, int64_t nrows, int64_t nsamples, const int32_t *__restrict__ perm,
+static __global__ void miss_list_kernel(const uint8_t *__restrict__ raw, int64_t nv, int64_t nrows, int64_t nsamples, const int32_t *__restrict__ perm,
                                  const FoldLayout *__restrict__ flp, const uint16_t *__restrict__ blk_desc, int64_t npos, int mcap,
                                  uint32_t *__restrict__ miss, int *__restrict__ max_cnt) {
     const FoldLayout &fl = *flp;
@@ -247,7 +249,7 @@ __global__ void miss_list_kernel(const uint8_t *__restrict__ raw, int64_t nv, in
 
 // Inverse of the packer for one SNP: byte masks in the reference's layout
 // [genotype][S_pad] (model.c:28-74).  One thread per bit position.
-__global__ void unpack_masks_kernel(const uint32_t *__restrict__ planes, int64_t snp, int64_t snp_pad,
+static __global__ void unpack_masks_kernel(const uint32_t *__restrict__ planes, int64_t snp, int64_t snp_pad,
                                     const int32_t *__restrict__ perm, const FoldLayout *__restrict__ flp, int64_t npos,
                                     int A, int a_pad, int s_pad, uint8_t *__restrict__ out) {
     const FoldLayout &fl = *flp;
@@ -450,7 +452,7 @@ __device__ __forceinline__ void dbg_add(const SearchArgs &a, int slot, unsigned 
     if (a.dbg) atomicAdd(a.dbg + slot, v);
 }
 // development trace of the offered tuples: (i, j), (fold, score, bound); out of line so that it costs the kernels no registers
-__device__ __noinline__ void dbg_trace(unsigned long long *dbg, int si, int sj, int f, long long score, long long thr) {
+static __device__ __noinline__ void dbg_trace(unsigned long long *dbg, int si, int sj, int f, long long score, long long thr) {
     const unsigned long long pos = atomicAdd(dbg + kDbgTraceCount, 1ULL);
     if (pos >= kDbgTraceCap) return;
     dbg[kDbgTrace + 2 * pos] = ((unsigned long long) (uint32_t) si << 32) | (uint32_t) sj;
@@ -785,7 +787,7 @@ __device__ __noinline__ void hist_count_tuple(SearchCtl *ctl, int *ghist, int *g
 }
 
 // a warp is through with its share of the CTA's first unit (counted only): the last one publishes the CTA's best pairs
-__device__ __noinline__ void first_unit_done(SearchCtl *ctl, int *ghist, int *ghmax, int *gfirst, int hist_bins, int nwarps, int lane) {
+static __device__ __noinline__ void first_unit_done(SearchCtl *ctl, int *ghist, int *ghmax, int *gfirst, int hist_bins, int nwarps, int lane) {
     __syncwarp();
     if (lane != 0) return;
     __threadfence_block();
@@ -1007,7 +1009,7 @@ __device__ __forceinline__ int warp_inclusive_scan(int v, int lane) {
     }
     return v;
 }
-__device__ __noinline__ void hist_threshold(SearchCtl *ctl, const int *ghist, const int *ghmax, long long *gthr, int hist_bins, int rank, int f, int lane) {
+static __device__ __noinline__ void hist_threshold(SearchCtl *ctl, const int *ghist, const int *ghmax, long long *gthr, int hist_bins, int rank, int f, int lane) {
     const int hmax = __ldcg(ghmax + f);
     const int cur = *reinterpret_cast<volatile int *>(&ctl->tq[f]);
     if (hmax < 0 || hmax < cur) return;
@@ -1832,6 +1834,393 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) search3v2_kernel(const Sear
 }
 
 // ============================================================================
+// Order 3, balanced cohorts: one thread per triple, pair table in registers, two-pass epilogue
+// ============================================================================
+// Same tiling and staging as search3v2_kernel (unit = (TJ j rows, 32 k rows) resident, i rows streamed), but ONE thread
+// counts both planes (0 and 1') of SNP i for its triple -- 18 cells, 18 x F counter words in its private slice -- and
+// keeps the pair table n_jk (9 x F words, constant over the whole i loop of a unit) in REGISTERS: with eight warps per CTA
+// a thread may use 255 of them.  Plane 1' = "genotype 1 or missing" of SNP i (valid & ~plane 0 & ~plane 2, one LOP3 per
+// word; `valid` = the bit positions of a block that hold samples), so
+//     n(2, gb, gc) = n_jk(gb, gc) - n(0, gb, gc) - n(1', gb, gc)
+// is exact whatever is missing where, and what remains is to take the samples SNP i is missing out of n(1', ., .).  The
+// epilogue does that in two passes over the cells, which needs no second table, no atomics and no undo:
+//   pass 1  cells of genotypes 0 and 2 of SNP i (from n0, n1', n_jk)  ->  partial pre-filter sums t_f
+//   fix-up  the thread's own table: n1' -> n1, one plain read-modify-write per missing sample of SNP i
+//   pass 2  cells of genotype 1 (from n1)                             ->  t_f complete, compared with the fold's bound
+// Only folds that pass (a handful per million triples) get the exact epilogue (risky cells, TP / FP, accuracy, list).
+struct Smem3bMap {
+    size_t tile, ring0, stage_bytes, stage_rows_bytes, vmask, counters, desc, lists, total;
+};
+__host__ __device__ inline Smem3bMap search3v3_smem_map(const FoldLayout &fl, int tj, int ni, int mcap, int rank, bool lists_in_smem) {
+    Smem3bMap m;
+    const size_t snp_bytes = (size_t) fl.nchunks * fl.row_words * 4;
+    m.tile = align_up(sizeof(SearchCtl), 128);
+    m.ring0 = m.tile + align_up((size_t) (tj + kTileJ) * snp_bytes, 128);
+    m.stage_rows_bytes = (size_t) ni * snp_bytes;
+    m.stage_bytes = align_up(m.stage_rows_bytes + (size_t) ni * mcap * 4, 128);
+    m.vmask = m.ring0 + 2 * m.stage_bytes;
+    m.counters = align_up(m.vmask + (size_t) fl.nblocks * slot_words(fl.w7 ? 7 : fl.bw) * 4, 16);
+    const int nwc = fl.single ? fl.nblocks / 4 : fl.F;
+    m.desc = m.counters + (size_t) counter_stride(18, nwc) * 4 * (size_t) (tj * 32);
+    m.lists = align_up(m.desc + (fl.single ? 0 : (size_t) fl.nblocks * 2), 16);
+    m.total = m.lists + (lists_in_smem ? (size_t) fl.F * rank * sizeof(Cand) : 0);
+    return m;
+}
+
+// risk flags, TP / FP and risky-cell bits of nine cells of one fold (balanced cohorts): tot / in_of as in balanced_fold
+template <int BITBASE, bool TRAINING, typename InOf>
+__device__ __forceinline__ void risk_cells9(const uint32_t (&tot)[9], InOf in_of, uint32_t &tpfp, uint32_t &mask) {
+    auto cell = [&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        const uint32_t in = in_of(c);
+        const uint32_t tr = tot[c] - in;
+        const int d = dp2a_lo_us(tr, 0x0000FF01u, 0);
+        risk_accumulate<(1u << (BITBASE + c))>(d, tr, TRAINING ? tr : in, tpfp, mask);
+    };
+    static_for<9>(cell);
+}
+
+template <int BW, bool SINGLE, int NWCMAX>
+__global__ void __launch_bounds__(256, 1) search3v3_kernel(const SearchArgs a) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    SearchCtl *ctl = reinterpret_cast<SearchCtl *>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int TJ = blockDim.x >> 5, jw = warp;
+    const int NI = a.v2_ni;
+    constexpr int NS = 2;
+    const Smem3bMap sm = search3v3_smem_map(*a.fl, TJ, NI, a.v2_mcap, a.rank, a.lists_in_smem != 0);
+    uint32_t *cnt_base = reinterpret_cast<uint32_t *>(smem_raw + sm.counters);
+    uint32_t *vmask = reinterpret_cast<uint32_t *>(smem_raw + sm.vmask);
+    uint16_t *desc = reinterpret_cast<uint16_t *>(smem_raw + sm.desc);
+    Cand *lists = a.lists_in_smem ? reinterpret_cast<Cand *>(smem_raw + sm.lists) : a.lists + (size_t) blockIdx.x * a.fl->F * a.rank;
+    search_init<SINGLE>(ctl, a, cnt_base, (sm.desc - sm.counters) / 4, desc);      // (barriers: full/empty[0..1] = the ring, full[2] = the tile)
+    constexpr int SW = slot_words(BW);
+    const int nblocks = ctl->fl.nblocks, cb = ctl->fl.cb, nchunks = ctl->fl.nchunks, roww = ctl->fl.row_words, F = ctl->fl.F;
+    for (int x = tid; x < nblocks * SW; x += blockDim.x) vmask[x] = a.v3_vmask[x];
+    __syncthreads();
+    const int nwc = SINGLE ? nblocks / 4 : F;
+    const int stride = counter_stride(18, nwc);
+    const uint32_t row_bytes = (uint32_t) roww * 4;
+    const int tile_rows = TJ + kTileJ;
+
+    // ---- step sequencing: as in search3v2_kernel ----
+    long long u = blockIdx.x;
+    int cur_j0 = 0, cur_k0 = 0, cur_i = 0, cur_iend = 0;
+    bool fresh = false;
+    auto decode = [&]() {
+        const int2 d = __ldg(a.unit_desc + u);
+        cur_j0 = d.x; cur_k0 = d.y;
+        cur_i = a.edge_lo;
+        cur_iend = min(a.edge_hi, min(cur_j0 + TJ - 2, a.nv - 3)) + 1;
+        fresh = true;
+    };
+    auto next_desc = [&]() {
+        for (;;) {
+            if (u >= a.num_units) return make_int4(-1, 0, 0, 0);
+            if (cur_i < cur_iend) {
+                const int n = min(NI, cur_iend - cur_i);
+                const int4 d = make_int4(cur_i, cur_j0, cur_k0, n | (fresh ? 1 << 16 : 0));
+                cur_i += n; fresh = false;
+                return d;
+            }
+            u += gridDim.x;
+            if (u < a.num_units) decode();
+        }
+    };
+    auto issue_tile = [&](int j0, int k0) {
+        uint8_t *dst = smem_raw + sm.tile;
+        mbar_arrive_expect_tx(&ctl->full[2], (uint32_t) nchunks * tile_rows * row_bytes);
+        for (int ch = 0; ch < nchunks; ch++) {
+            const char *src = reinterpret_cast<const char *>(a.planes) + (int64_t) ch * a.snp_pad * row_bytes;
+            bulk_g2s(dst + (size_t) ch * tile_rows * row_bytes, src + (int64_t) j0 * row_bytes, (uint32_t) TJ * row_bytes, &ctl->full[2]);
+            bulk_g2s(dst + ((size_t) ch * tile_rows + TJ) * row_bytes, src + (int64_t) k0 * row_bytes, (uint32_t) kTileJ * row_bytes, &ctl->full[2]);
+        }
+    };
+    auto issue_rows = [&](int st, int i0) {
+        uint8_t *dst = smem_raw + sm.ring0 + (size_t) st * sm.stage_bytes;
+        mbar_arrive_expect_tx(&ctl->full[st], (uint32_t) (nchunks * NI) * row_bytes + (uint32_t) (NI * a.v2_mcap * 4));
+        for (int ch = 0; ch < nchunks; ch++) {
+            const char *src = reinterpret_cast<const char *>(a.planes) + (int64_t) ch * a.snp_pad * row_bytes;
+            bulk_g2s(dst + (size_t) ch * NI * row_bytes, src + (int64_t) i0 * row_bytes, (uint32_t) NI * row_bytes, &ctl->full[st]);
+        }
+        bulk_g2s(dst + sm.stage_rows_bytes, a.v2_miss + (int64_t) i0 * a.v2_mcap, (uint32_t) (NI * a.v2_mcap * 4), &ctl->full[st]);
+    };
+    const bool producer = (tid == blockDim.x - 32);
+    if (producer) {
+        if (u < a.num_units) decode();
+        const int4 d = next_desc();
+        ctl->meta[0] = d;
+        if (d.x >= 0) { issue_tile(d.y, d.z); issue_rows(0, d.x); }
+        else mbar_arrive(&ctl->full[0]);
+    }
+
+    uint32_t *mine = cnt_base + (size_t) (jw * 32 + lane) * stride;      // word (kk, c): mine[kk * 18 + c], c < 9: n0, else n1
+    const uint32_t *tile = reinterpret_cast<const uint32_t *>(smem_raw + sm.tile);
+    uint32_t njk[NWCMAX][9], totjk[9];
+#pragma unroll
+    for (int kk = 0; kk < NWCMAX; kk++)
+#pragma unroll
+        for (int c = 0; c < 9; c++) njk[kk][c] = 0;
+#pragma unroll
+    for (int c = 0; c < 9; c++) totjk[c] = 0;
+    uint32_t tile_phase = 0;
+
+    // totals (cases | controls << 16) of a counter word over the folds it holds
+    auto word_total = [&](uint32_t w) -> uint32_t {
+        if constexpr (SINGLE) return __dp4a(w, 0x00000101u, 0u) | (__dp4a(w, 0x01010000u, 0u) << 16);
+        else return w;
+    };
+    // counts (PAIR: the nine cells of the pair table; else the 18 cells of planes 0 and 1' of the staged row) into dst
+    auto count_tables = [&](auto pair_tag, const uint32_t *irows, int istride, uint32_t *dst) {
+        constexpr bool PAIR = decltype(pair_tag)::value;
+        uint32_t acc0[9], acc1[9];
+#pragma unroll
+        for (int c = 0; c < 9; c++) { acc0[c] = 0; acc1[c] = 0; }
+        for (int ch = 0; ch < nchunks; ch++) {
+            const uint32_t *jr = tile + ((size_t) ch * tile_rows + jw) * roww;
+            const uint32_t *kr = tile + ((size_t) ch * tile_rows + TJ + lane) * roww;
+            const uint32_t *ir = irows + (size_t) ch * istride;
+            const int b_lo = ch * cb, b_hi = min(nblocks, b_lo + cb);
+            for (int b = b_lo; b < b_hi; b++) {
+                const int off = (b - b_lo) * 3 * SW;
+                uint32_t pl[3][BW], p0[BW], p1[BW];
+#pragma unroll
+                for (int g = 0; g < 3; g++) load_plane<BW>(kr + off + g * SW, pl[g]);
+                if constexpr (!PAIR) {
+                    uint32_t p2[BW], vm[BW];
+                    load_plane<BW>(ir + off, p0);
+                    load_plane<BW>(ir + off + 2 * SW, p2);
+                    load_plane<BW>(vmask + b * SW, vm);
+#pragma unroll
+                    for (int w = 0; w < BW; w++) asm("lop3.b32 %0, %1, %2, %3, 0x10;" : "=r"(p1[w]) : "r"(vm[w]), "r"(p0[w]), "r"(p2[w]));   // valid & ~p0 & ~p2
+                }
+                const uint32_t kq = SINGLE ? (1u << group_shift_rt((uint32_t) b & 3u)) : 1u;
+#pragma unroll
+                for (int gb = 0; gb < 3; gb++) {
+                    uint32_t pj[BW];
+                    load_plane<BW>(jr + off + gb * SW, pj);
+#pragma unroll
+                    for (int gc = 0; gc < 3; gc++) {
+                        const int c = gb * 3 + gc;
+                        if constexpr (PAIR) {
+                            if constexpr (SINGLE) acc0[c] += cell_count2_acc<BW, 1u>(pj, pl[gc], 0u) * kq;
+                            else acc0[c] = cell_count2_acc<BW, 1u>(pj, pl[gc], acc0[c]);
+                        } else if constexpr (SINGLE) {
+                            acc0[c] += cell_count3_acc<BW, 1u>(p0, pj, pl[gc], 0u) * kq;
+                            acc1[c] += cell_count3_acc<BW, 1u>(p1, pj, pl[gc], 0u) * kq;
+                        } else {
+                            acc0[c] = cell_count3_acc<BW, 1u>(p0, pj, pl[gc], acc0[c]);
+                            acc1[c] = cell_count3_acc<BW, 1u>(p1, pj, pl[gc], acc1[c]);
+                        }
+                    }
+                }
+                if constexpr (SINGLE) {
+                    if ((b & 3) == 3) {
+#pragma unroll
+                        for (int c = 0; c < 9; c++) {
+                            dst[(b >> 2) * 18 + c] = acc0[c]; acc0[c] = 0;
+                            if constexpr (!PAIR) { dst[(b >> 2) * 18 + 9 + c] = acc1[c]; acc1[c] = 0; }
+                        }
+                    }
+                } else {
+                    const unsigned d = desc[b];
+                    if (d & 0x8000u) {
+                        const int seg = d & 0x7fff;
+#pragma unroll
+                        for (int c = 0; c < 9; c++) {
+                            reinterpret_cast<uint16_t *>(dst + (seg >> 1) * 18 + c)[seg & 1] = (uint16_t) acc0[c]; acc0[c] = 0;
+                            if constexpr (!PAIR) { reinterpret_cast<uint16_t *>(dst + (seg >> 1) * 18 + 9 + c)[seg & 1] = (uint16_t) acc1[c]; acc1[c] = 0; }
+                        }
+                    }
+                }
+            }
+        }
+    };
+
+    const uint32_t *miss = nullptr;
+    // the samples SNP i (row ii of the stage) is missing: out of (sign -1) / back into (+1) the thread's own table of plane 1'
+    auto missing_fixup = [&](int ii, int sign) {
+        const uint32_t *ml = miss + (size_t) ii * a.v2_mcap;
+        for (int m = 0; m < a.v2_mcap; m++) {
+            const uint32_t e = ml[m];
+            if (e == kMissEnd) break;
+            const int bit = e >> 27, off = (e >> 16) & 0x7ff, ch = (e >> 12) & 0xf, code = e & 0xfff;
+            const uint32_t *jr = tile + ((size_t) ch * tile_rows + jw) * roww + off;
+            const uint32_t *kr = tile + ((size_t) ch * tile_rows + TJ + lane) * roww + off;
+            const uint32_t j1 = (jr[SW] >> bit) & 1u, j2 = (jr[2 * SW] >> bit) & 1u, jv = ((jr[0] >> bit) & 1u) | j1 | j2;
+            const uint32_t k1 = (kr[SW] >> bit) & 1u, k2 = (kr[2 * SW] >> bit) & 1u, kv = ((kr[0] >> bit) & 1u) | k1 | k2;
+            if (jv & kv) {
+                const int c = (int) (j1 + 2 * j2) * 3 + (int) (k1 + 2 * k2);
+                uint32_t delta, *word;
+                if constexpr (SINGLE) { word = mine + (code & 0x3ff) * 18 + 9 + c; delta = 1u << group_shift_rt((uint32_t) code >> 10); }
+                else { word = mine + (code & 0x1f) * 18 + 9 + c; delta = 1u << (16 * (code >> 5)); }
+                *word += sign < 0 ? 0u - delta : delta;
+            }
+        }
+    };
+    auto njk_at = [&](int kk, int c) -> uint32_t {          // run-time kk (the rare exact path): select chain over the registers
+        uint32_t v = 0;
+#pragma unroll
+        for (int q = 0; q < NWCMAX; q++)
+#pragma unroll
+            for (int cc = 0; cc < 9; cc++) if (q == kk && cc == c) v = njk[q][cc];
+        return v;
+    };
+
+    constexpr int NF = SINGLE ? 2 * NWCMAX : NWCMAX;        // folds a thread may have to carry partial sums for
+    int st = 0;
+    uint32_t ph = 0;
+    for (uint32_t s = 0;; s++) {
+        const int nst = st ^ 1;
+        int4 next = make_int4(-1, 0, 0, 0);
+        if (producer) {
+            next = next_desc();
+            ctl->meta[(s + 1) & 3] = next;
+            if (s + 1 >= (uint32_t) NS && !(next.x >= 0 && (next.w >> 16))) mbar_wait(&ctl->empty[nst], ((s + 1 - NS) / NS) & 1);
+            if (next.x >= 0 && !(next.w >> 16)) issue_rows(nst, next.x);
+            else if (next.x < 0) mbar_arrive(&ctl->full[nst]);
+        }
+        __syncwarp();
+        mbar_wait(&ctl->full[st], ph);
+        const int4 meta = ctl->meta[s & 3];
+        if (meta.x < 0) break;
+        const int i0 = meta.x, j0 = meta.y, k0 = meta.z, ni = meta.w & 0xffff;
+        if (meta.w >> 16) {
+            // a new unit: count its pair table into the thread's slice, then take it into registers for the whole i loop
+            mbar_wait(&ctl->full[2], tile_phase);
+            tile_phase ^= 1u;
+            count_tables(std::true_type{}, tile, 0, mine);
+#pragma unroll
+            for (int c = 0; c < 9; c++) totjk[c] = 0;
+#pragma unroll
+            for (int kk = 0; kk < NWCMAX; kk++)
+                if (kk < nwc) {
+#pragma unroll
+                    for (int c = 0; c < 9; c++) { njk[kk][c] = mine[kk * 18 + c]; totjk[c] += word_total(njk[kk][c]); }
+                }
+        }
+        if ((s & 31) == 0 && lane < F && warp == (int) ((s >> 5) % (uint32_t) TJ)) refresh_threshold(ctl, a, lane);
+        const uint32_t *stage = reinterpret_cast<const uint32_t *>(smem_raw + sm.ring0 + (size_t) st * sm.stage_bytes);
+        miss = reinterpret_cast<const uint32_t *>(smem_raw + sm.ring0 + (size_t) st * sm.stage_bytes + sm.stage_rows_bytes);
+        const int j = j0 + jw, k = k0 + lane;
+        for (int ii = 0; ii < ni; ii++) {
+            const int i = i0 + ii;
+            count_tables(std::false_type{}, stage + (size_t) ii * roww, NI * roww, mine);
+            bool valid = (i < j) && (j < k) && (k < a.nv);
+            if (valid && (i <= a.edge_lo || i >= a.edge_hi)) {
+                const uint64_t idx = triple_index((uint64_t) a.nv, (uint64_t) i, (uint64_t) j, (uint64_t) k);
+                valid = idx >= a.first && idx < a.last;
+            }
+            if (!__any_sync(0xffffffffu, valid)) continue;
+
+            // ---- pass 1: cells of genotypes 0 and 2 of SNP i ----
+            uint32_t tot0[9], tot2[9];
+#pragma unroll
+            for (int c = 0; c < 9; c++) { tot0[c] = 0; tot2[c] = totjk[c]; }
+#pragma unroll
+            for (int kk = 0; kk < NWCMAX; kk++)
+                if (kk < nwc) {
+#pragma unroll
+                    for (int c = 0; c < 9; c++) {
+                        const uint32_t w0 = word_total(mine[kk * 18 + c]);
+                        tot0[c] += w0;
+                        tot2[c] -= w0 + word_total(mine[kk * 18 + 9 + c]);
+                    }
+                }
+            int t[NF];
+#pragma unroll
+            for (int f = 0; f < NF; f++) t[f] = 0;
+            if (a.prefilter) {
+                int D0[9], D2[9];
+#pragma unroll
+                for (int c = 0; c < 9; c++) { D0[c] = dp2a_lo_us(tot0[c], 0x0000FF01u, 0); D2[c] = dp2a_lo_us(tot2[c], 0x0000FF01u, 0); }
+#pragma unroll
+                for (int kk = 0; kk < NWCMAX; kk++)
+                    if (kk < nwc) {
+#pragma unroll
+                        for (int c = 0; c < 9; c++) {
+                            const uint32_t w0 = mine[kk * 18 + c], w2 = njk[kk][c] - w0 - mine[kk * 18 + 9 + c];
+                            if constexpr (SINGLE) {
+                                t[2 * kk] += max(dp4a_us(w0, 0x000100FFu, D0[c]), 0) + max(dp4a_us(w2, 0x000100FFu, D2[c]), 0);
+                                t[2 * kk + 1] += max(dp4a_us(w0, 0x0100FF00u, D0[c]), 0) + max(dp4a_us(w2, 0x0100FF00u, D2[c]), 0);
+                            } else {
+                                t[kk] += max(dp2a_lo_us(w0, 0x000001FFu, D0[c]), 0) + max(dp2a_lo_us(w2, 0x000001FFu, D2[c]), 0);
+                            }
+                        }
+                    }
+            }
+            // ---- the thread's own table of plane 1': out go the samples SNP i is missing ----
+            missing_fixup(ii, -1);
+            // ---- pass 2: cells of genotype 1 ----
+            uint32_t tot1[9];
+#pragma unroll
+            for (int c = 0; c < 9; c++) tot1[c] = 0;
+#pragma unroll
+            for (int kk = 0; kk < NWCMAX; kk++)
+                if (kk < nwc) {
+#pragma unroll
+                    for (int c = 0; c < 9; c++) tot1[c] += word_total(mine[kk * 18 + 9 + c]);
+                }
+            unsigned pass_folds = 0xffffffffu;                   // without the pre-filter every fold gets the exact epilogue
+            if (a.prefilter) {
+                int D1[9];
+#pragma unroll
+                for (int c = 0; c < 9; c++) D1[c] = dp2a_lo_us(tot1[c], 0x0000FF01u, 0);
+#pragma unroll
+                for (int kk = 0; kk < NWCMAX; kk++)
+                    if (kk < nwc) {
+#pragma unroll
+                        for (int c = 0; c < 9; c++) {
+                            const uint32_t w1 = mine[kk * 18 + 9 + c];
+                            if constexpr (SINGLE) {
+                                t[2 * kk] += max(dp4a_us(w1, 0x000100FFu, D1[c]), 0);
+                                t[2 * kk + 1] += max(dp4a_us(w1, 0x0100FF00u, D1[c]), 0);
+                            } else {
+                                t[kk] += max(dp2a_lo_us(w1, 0x000001FFu, D1[c]), 0);
+                            }
+                        }
+                    }
+                pass_folds = 0;
+#pragma unroll
+                for (int f = 0; f < NF; f++)
+                    if (f < F && __any_sync(0xffffffffu, valid && t[f] >= *reinterpret_cast<volatile int *>(&ctl->tq[f]))) pass_folds |= 1u << f;
+            }
+            // ---- exact epilogue of the folds that passed (rare) ----
+            for (int f = 0; f < F; f++) {
+                if (!((pass_folds >> f) & 1u)) continue;
+                const int kk = SINGLE ? (f >> 1) : f;
+                uint32_t tpfp = 0, mask = 0;
+                auto in1 = [&](int c) -> uint32_t { return fold_pair<SINGLE>(mine[kk * 18 + 9 + c], f); };
+                if (a.training) risk_cells9<9, true>(tot1, in1, tpfp, mask); else risk_cells9<9, false>(tot1, in1, tpfp, mask);
+                missing_fixup(ii, +1);                           // back to plane 1': the derived cells are exact against it
+                auto in0 = [&](int c) -> uint32_t { return fold_pair<SINGLE>(mine[kk * 18 + c], f); };
+                auto in2 = [&](int c) -> uint32_t { return fold_pair<SINGLE>(njk_at(kk, c) - mine[kk * 18 + c] - mine[kk * 18 + 9 + c], f); };
+                if (a.training) { risk_cells9<0, true>(tot0, in0, tpfp, mask); risk_cells9<18, true>(tot2, in2, tpfp, mask); }
+                else { risk_cells9<0, false>(tot0, in0, tpfp, mask); risk_cells9<18, false>(tot2, in2, tpfp, mask); }
+                missing_fixup(ii, -1);
+                const int tp = (int) (tpfp & 0xffffu), fp = (int) (tpfp >> 16);
+                const int npos = a.training ? ctl->fl.A - ctl->fl.a_in[f] : ctl->fl.a_in[f];
+                const int nneg = a.training ? ctl->fl.U - ctl->fl.u_in[f] : ctl->fl.u_in[f];
+                const bool degenerate = (npos == 0 || nneg == 0);
+                const long long score = degenerate ? LLONG_MIN
+                                        : (a.eval_fn == kEvalBA ? ba_score(tp, fp, npos, nneg) : value_score(evaluate_fn(a.eval_fn, tp, npos - tp, fp, nneg - fp)));
+                offer_fold(ctl, a, lists, f, valid, score, degenerate, npos, nneg, i, j, k, mask, tp, fp, lane);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->empty[st]);
+        if (producer && next.x >= 0 && (next.w >> 16)) {
+            mbar_wait(&ctl->empty[st], (s / NS) & 1);
+            issue_tile(next.y, next.z);
+            issue_rows(nst, next.x);
+        }
+        st = nst;
+        if (st == 0) ph ^= 1u;
+    }
+    search_publish(ctl, a, lists);
+}
+
+// ============================================================================
 // Merge: many partial top-N lists -> the final top-N of every fold
 // ============================================================================
 // One CTA per fold.  Every entry gets a 128-bit key that realises the canonical
@@ -1871,7 +2260,7 @@ constexpr int kMergeThreads = 1024;
 constexpr int kMergeSmall = 2048;        // up to this many valid entries per fold are ranked by counting in shared memory
 __host__ __device__ inline size_t merge_smem_bytes(int rank_out) { return (size_t) rank_out * 20 + 16 + (size_t) kMergeSmall * 20; }
 
-__global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeArgs m) {
+static __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeArgs m) {
     extern __shared__ __align__(16) uint8_t msmem[];
     Key128 *selkey = reinterpret_cast<Key128 *>(msmem);                       // [rank_out]
     int *selidx = reinterpret_cast<int *>(msmem + (size_t) m.rank_out * 16);   // [rank_out]
@@ -2003,7 +2392,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeArgs m)
 }
 
 // hpgv_epi_model_t lists (all-gathered from the ranks) -> Cand lists for merge_kernel
-__global__ void models_to_cands_kernel(const ModelOut *in, int64_t n, Cand *out) {
+static __global__ void models_to_cands_kernel(const ModelOut *in, int64_t n, Cand *out) {
     const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const ModelOut r = in[t];
@@ -2017,7 +2406,7 @@ __global__ void models_to_cands_kernel(const ModelOut *in, int64_t n, Cand *out)
 // ============================================================================
 // Parity hook: explicit combinations, one warp each (simple on purpose)
 // ============================================================================
-__global__ void eval_kernel(const uint32_t *__restrict__ planes, const uint16_t *__restrict__ blk_desc,
+static __global__ void eval_kernel(const uint32_t *__restrict__ planes, const uint16_t *__restrict__ blk_desc,
                             const FoldLayout *__restrict__ flp, int64_t snp_pad, int order, int training, int eval_fn,
                             int64_t ncomb, const int32_t *__restrict__ combs, const uint32_t *__restrict__ risky_in,
                             int32_t *counts_aff, int32_t *counts_unaff, uint32_t *risky_mask, uint32_t *conf, double *acc) {
@@ -2078,14 +2467,14 @@ __global__ void eval_kernel(const uint32_t *__restrict__ planes, const uint16_t 
 }
 
 // the device high-risk rule on explicit count pairs, and evaluate_model on explicit confusion matrices (parity hooks)
-__global__ void high_risk_kernel(const int32_t *__restrict__ ca, const int32_t *__restrict__ cu, int64_t n, int A, int U, int32_t *__restrict__ flags) {
+static __global__ void high_risk_kernel(const int32_t *__restrict__ ca, const int32_t *__restrict__ cu, int64_t n, int A, int U, int32_t *__restrict__ flags) {
     const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     RiskParams rp;
     rp.balanced = (A == U); rp.A = A; rp.U = U; rp.ratio = (float) A / (float) U;          // mdr.c:52
     flags[t] = high_risk(ca[t], cu[t], rp) ? 1 : 0;
 }
-__global__ void evaluate_kernel(int eval_fn, int64_t n, const uint32_t *__restrict__ conf, double *__restrict__ out) {
+static __global__ void evaluate_kernel(int eval_fn, int64_t n, const uint32_t *__restrict__ conf, double *__restrict__ out) {
     const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     out[t] = evaluate_fn(eval_fn, (int) conf[4 * t], (int) conf[4 * t + 1], (int) conf[4 * t + 2], (int) conf[4 * t + 3]);

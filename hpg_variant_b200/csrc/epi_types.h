@@ -123,6 +123,7 @@ struct SearchArgs {
     // search3v2_kernel: rows of NI SNPs i per stage, per-SNP lists of missing samples (v2_mcap entries each)
     int v2_ni, v2_mcap;
     const uint32_t *v2_miss;    // [snp_pad][v2_mcap], see kMissEnd
+    const uint32_t *v3_vmask;   // search3v3_kernel: [nblocks][slot words] the bit positions of every block that hold a sample
     int eval_fn;                // enum eval_function of model.h:84 (kEval* in epi_device.cuh); 1 = BA, the reference runner's choice (model.c:331)
     int prefilter;              // balanced classes, equal folds, TRAINING part and BA: the pre-filter of epilogue_balanced_t applies
     int tri_derive;             // derive genotype 2 of SNP i from SNP j's marginals in blocks where i has no missing sample (rows with marg)

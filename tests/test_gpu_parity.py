@@ -146,6 +146,28 @@ def test_search_order3_resident_tiles(engine, oracle, monkeypatch, nv, A, U, F, 
         engine.set_folds(F, fos)
         plain = engine.search(3, subset, rank)
         assert plain.tobytes() == got.tobytes()
+        monkeypatch.delenv("HPGV_SEARCH3_V2", raising=False)
+        monkeypatch.setenv("HPGV_SEARCH3_V3", "1")            # the one-thread-per-triple kernel (opt-in) where it applies
+        engine.set_folds(F, fos)
+        one = engine.search(3, subset, rank)
+        monkeypatch.delenv("HPGV_SEARCH3_V3", raising=False)
+        assert one.tobytes() == got.tobytes()
+
+
+@pytest.mark.parametrize("nv,A,F", [(34, 1000, 10), (30, 2400, 10), (32, 200, 7)])     # (10 folds of 16-bit counters: outside what v3 was built for)
+def test_search_order3_one_thread_kernel_fold_counts(engine, oracle, monkeypatch, nv, A, F):
+    """search3v3_kernel (HPGV_SEARCH3_V3=1) with other counter shapes than c4's: 10 folds of byte counters (5 words per cell), 7
+    folds of 4-word blocks (odd fold count); 10 folds of 16-bit counters fall back to the default kernel, which is also run
+    on all three shapes."""
+    g = synth.make_dataset(nv, A, A, seed=nv + F, order=3, missing=0.01, planted=1)
+    fos, _ = h.k_folds(A, A, F, seed=8)
+    want, _ = oracle.search(g, A, A, 3, fos, h.SUBSET_TRAINING, 30, threads=8, num_folds=F)
+    for v3 in ("1", "0"):
+        monkeypatch.setenv("HPGV_SEARCH3_V3", v3)
+        engine.load_dataset(g, A, A)
+        engine.set_folds(F, fos)
+        got = engine.search(3, h.SUBSET_TRAINING, 30)
+        compare_models(got, want, 3)
 
 
 def test_search_order3_resident_tiles_many_units(engine, monkeypatch):
@@ -157,11 +179,13 @@ def test_search_order3_resident_tiles_many_units(engine, monkeypatch):
     engine.load_dataset(g, A, A)
     engine.set_folds(F, fos)
     got = [engine.search(3, h.SUBSET_TRAINING, rank), engine.search(3, h.SUBSET_TRAINING, rank, total // 3, total // 3 * 2 + 11)]
-    monkeypatch.setenv("HPGV_SEARCH3_V2", "0")
-    engine.set_folds(F, fos)
-    plain = [engine.search(3, h.SUBSET_TRAINING, rank), engine.search(3, h.SUBSET_TRAINING, rank, total // 3, total // 3 * 2 + 11)]
-    for a, b in zip(got, plain):
-        assert a.tobytes() == b.tobytes()
+    for switch, val in (("HPGV_SEARCH3_V2", "0"), ("HPGV_SEARCH3_V3", "1")):
+        monkeypatch.setenv(switch, val)
+        engine.set_folds(F, fos)
+        other = [engine.search(3, h.SUBSET_TRAINING, rank), engine.search(3, h.SUBSET_TRAINING, rank, total // 3, total // 3 * 2 + 11)]
+        monkeypatch.delenv(switch, raising=False)
+        for a, b in zip(got, other):
+            assert a.tobytes() == b.tobytes()
 
 
 @pytest.mark.parametrize("order,nv,A,F", [(2, 80, 600, 6), (3, 22, 240, 4)])
