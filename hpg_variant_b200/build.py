@@ -19,7 +19,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-ccbin", "g++",
 ]
 # one translation unit per kernel family (compiled in parallel: the search kernels dominate the build) + the C-ABI
-CUDA_UNITS = ["epi_capi.cu", "epi_k_search2.cu", "epi_k_search3.cu", "epi_k_search3v2.cu", "epi_k_search3v3.cu"]
+CUDA_UNITS = ["epi_capi.cu", "epi_k_search2.cu", "epi_k_search2_tri.cu", "epi_k_search3.cu", "epi_k_search3v2.cu", "epi_k_search3v3.cu"]
 
 
 def _newer(target, sources):

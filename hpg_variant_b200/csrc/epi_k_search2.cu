@@ -4,14 +4,16 @@
 
 namespace hpgv {
 
+search_kernel_t kernel_search2_tri(bool balanced);          // epi_k_search2_tri.cu
+
 search_kernel_t kernel_search2(int bw, bool single, bool balanced) {
+    if (bw == 3) return kernel_search2_tri(balanced);
 #define HPGV_VARIANT(BW, SINGLE) if (bw == BW && single == SINGLE) return balanced ? (search_kernel_t) search2_kernel<BW, SINGLE, true> : (search_kernel_t) search2_kernel<BW, SINGLE, false>
     HPGV_VARIANT(4, true);
     HPGV_VARIANT(7, true);
     HPGV_VARIANT(7, false);
     HPGV_VARIANT(8, true);
     HPGV_VARIANT(8, false);
-    HPGV_VARIANT(3, true);                       // the tri layout
 #undef HPGV_VARIANT
     return nullptr;
 }

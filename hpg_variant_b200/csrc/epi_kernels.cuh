@@ -285,6 +285,15 @@ __device__ __forceinline__ Key128 make_key(double ba, int i, int j, int k) {    
 }
 __device__ __forceinline__ Key128 cand_key(const Cand &c, int order) { return make_key(c.ba, c.i, c.j, order == 2 ? -1 : c.k); }
 
+// step sequencing of search2_kernel (used by the producer lane only)
+struct ProducerState {
+    long long u, pre_u;            // current unit; unit whose descriptor `pre` was loaded one unit ahead
+    int2 pre;
+    int grp, chunk, cur_i0, cur_j0;
+    int redo;                      // 0: main pass, 1: re-running the first unit, 2: no more work
+    int started;
+};
+
 struct __align__(16) SearchCtl {
     uint64_t full[3];              // per stage (two or three are in use): the chunk rows have landed
     uint64_t empty[3];             // per stage: every warp is done reading it
@@ -302,6 +311,8 @@ struct __align__(16) SearchCtl {
     int first_best[kMaxFolds];     // best pre-filter score of the CTA's first unit, per fold (-1: none); see hist_count_tuple
     int first_done;                // warps that are through with the CTA's first unit
     FoldLayout fl;
+    ProducerState ps;              // the tri kernel keeps its step sequencing here instead of in registers (HPGV_PS_IN_SMEM); last
+                                   // member on purpose: the other kernels' code (offsets of everything above) stays as it was
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -1105,6 +1116,49 @@ __global__ void __launch_bounds__((SINGLE ? kTriWarps : kMaxWarps) * 32, 1) sear
     const int nwc = SINGLE ? nblocks / 4 : ctl->fl.F;
     const uint32_t row_bytes = (uint32_t) roww * 4;
 
+#ifdef HPGV_PS_IN_SMEM
+    // ---- step sequencing (producer lane), state in shared memory (SearchCtl::ps) ----
+    // This translation unit is compiled with HPGV_PS_IN_SMEM (epi_k_search2_tri.cu: the tri kernel, 96 registers, 20 warps):
+    // as locals the state cost every thread a dozen registers in the counting loop, spills included (c2: 5.23 -> 5.05 ms).
+    // The other variants have the registers and are 2 % faster with plain locals (c3, measured): they take the #else branch.
+    ProducerState &ps = ctl->ps;
+    if (tid == nthreads - 32) {
+        ps.u = blockIdx.x; ps.pre_u = -1; ps.pre = make_int2(0, 0);
+        ps.grp = 0; ps.chunk = 0; ps.cur_i0 = 0; ps.cur_j0 = 0; ps.redo = 0; ps.started = 0;
+    }
+    auto decode = [&]() {
+        if (a.unit_desc) {
+            const int2 d = ps.pre_u == ps.u ? ps.pre : __ldg(a.unit_desc + ps.u);
+            ps.cur_i0 = d.x; ps.cur_j0 = d.y;
+            ps.pre_u = ps.u + gridDim.x;
+            if (ps.pre_u < a.num_units) ps.pre = __ldg(a.unit_desc + ps.pre_u);     // lands while the CTA counts
+            return;
+        }
+        while (ps.grp + 1 < a.n_it && a.unit_prefix[ps.grp + 1] <= ps.u) ps.grp++;
+        ps.cur_i0 = (a.it0 + ps.grp) * TI;
+        ps.cur_j0 = (a.unit_jt0[ps.grp] + (int) (ps.u - a.unit_prefix[ps.grp])) * kTileJ;
+    };
+    auto mode_of = [&]() { return !a.use_hist || ps.redo ? kModeOffer : (ps.u == (long long) blockIdx.x ? kModeCount : (kModeCount | kModeOffer)); };
+    auto next_desc = [&]() {                        // descriptors in step order, one per call; x = -1 once the work is done
+        if (!ps.started) {
+            ps.started = 1;
+            if (ps.u < a.num_units) { decode(); return make_int4(0, ps.cur_i0, ps.cur_j0, mode_of()); }
+            ps.redo = 2;
+        }
+        if (ps.redo == 2) return make_int4(-1, 0, 0, 0);
+        if (++ps.chunk == nchunks) {
+            ps.chunk = 0;
+            if (ps.redo == 1) { ps.redo = 2; return make_int4(-1, 0, 0, 0); }
+            ps.u += gridDim.x;
+            if (ps.u >= a.num_units) {
+                if (!a.use_hist) { ps.redo = 2; return make_int4(-1, 0, 0, 0); }
+                ps.redo = 1; ps.u = blockIdx.x; ps.grp = 0;
+            }
+            decode();
+        }
+        return make_int4(ps.chunk, ps.cur_i0, ps.cur_j0, mode_of());
+    };
+#else
     // ---- step sequencing (thread 0): units blockIdx.x, blockIdx.x + gridDim.x, ... each cut into nchunks steps ----
     long long u = blockIdx.x;
     int grp = 0, chunk = 0, cur_i0 = 0, cur_j0 = 0;
@@ -1146,6 +1200,7 @@ __global__ void __launch_bounds__((SINGLE ? kTriWarps : kMaxWarps) * 32, 1) sear
         }
         return make_int4(chunk, cur_i0, cur_j0, mode_of());
     };
+#endif
     auto issue = [&](int st, int ch, int i0, int j0) {
         uint8_t *dst = smem_raw + sm.stage0 + (size_t) st * sm.stage_bytes;
         const char *src = reinterpret_cast<const char *>(a.planes) + (int64_t) ch * a.snp_pad * row_bytes;
