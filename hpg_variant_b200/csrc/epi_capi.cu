@@ -658,7 +658,10 @@ static SearchShape pick_shape(const hpgv_epi_ctx *ctx, int order, int rank) {
     SearchShape best;
     const char *tw_env = getenv("HPGV_TRI_WARPS");               // A/B switch: "16" keeps the tri kernel at 16 warps
     const bool tri20 = order == 2 && fl.single && !(tw_env && tw_env[0] == '1' && tw_env[1] == '6');
-    for (int warps = tri20 ? kTriWarps : kMaxWarps; warps >= 1; warps = (warps == kTriWarps ? kMaxWarps : warps >> 1)) {
+    // 20 (byte-counter order-2 kernels), 16, then for order 2 also 12 and 10 (c5: 90 counter words per thread leave room for ten
+    // warps, not for sixteen), 8, 4, 2, 1
+    auto next_warps = [&](int w) { return w == kTriWarps ? kMaxWarps : ((order == 2 && w == 16) ? 12 : ((order == 2 && w == 12) ? 10 : (w == 10 ? 8 : w >> 1))); };
+    for (int warps = tri20 ? kTriWarps : kMaxWarps; warps >= 1; warps = next_warps(warps)) {
         const int rows = order == 2 ? warps + kTileJ : 1 + warps + kTileJ;
         for (int in_smem = 1; in_smem >= 0; in_smem--) {
             if (in_smem && (size_t) fl.F * rank * sizeof(Cand) > 24 * 1024) continue;
