@@ -456,13 +456,21 @@ static int apply_folds(hpgv_epi_ctx *ctx, int F, const int32_t *fold_of_sample, 
     // (the tri layout's marginals are only written by the staged packer; its permutation always fits)
     if (pm.total <= 96 * 1024 && (fl.tri || !(old_packer && old_packer[0] == '1'))) {
         // several CTAs per SM hide the latency of the row loads; each walks SNPs blockIdx.x, + gridDim.x, ...
-        if (pm.total > 48 * 1024) CK(cudaFuncSetAttribute(pack_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pm.total));
+        if (pm.total > 48 * 1024) {
+            CK(cudaFuncSetAttribute(pack_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pm.total));
+            CK(cudaFuncSetAttribute(pack_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pm.total));
+        }
         const int per_sm = (int) std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / pm.total));
         const int64_t batches = (ctx->nv + kPackRows - 1) / kPackRows;
         int64_t grid = std::min<int64_t>(batches, (int64_t) ctx->num_sms * per_sm);
         grid = (batches + (batches + grid - 1) / grid - 1) / ((batches + grid - 1) / grid);     // every CTA the same number of batches
-        pack_rows_kernel<<<(unsigned) grid, threads, pm.total, ctx->stream>>>(ctx->d_raw, ctx->nv, S, ctx->d_perm.p, ctx->d_fl.p, ctx->snp_pad,
-                                                                              ctx->npos, ctx->d_planes.p);
+        const char *gp = getenv("HPGV_PACK_GENERIC");            // A/B switch: "1" packs the tri layout with the generic path
+        if (fl.tri && !(gp && gp[0] == '1'))
+            pack_rows_kernel<true><<<(unsigned) grid, threads, pm.total, ctx->stream>>>(ctx->d_raw, ctx->nv, S, ctx->d_perm.p, ctx->d_fl.p,
+                                                                                        ctx->snp_pad, ctx->npos, ctx->d_planes.p);
+        else
+            pack_rows_kernel<false><<<(unsigned) grid, threads, pm.total, ctx->stream>>>(ctx->d_raw, ctx->nv, S, ctx->d_perm.p, ctx->d_fl.p,
+                                                                                         ctx->snp_pad, ctx->npos, ctx->d_planes.p);
     } else {
         const int64_t warps = ctx->nv * (int64_t) nb * fl.bw;
         const int64_t blocks = (warps * 32 + threads - 1) / threads;

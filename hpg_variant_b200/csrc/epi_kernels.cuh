@@ -94,6 +94,10 @@ __host__ __device__ inline PackSmem pack_smem_map(int64_t npos, int64_t nsamples
     m.total = m.out + (size_t) kPackRows * fl.nchunks * fl.row_words * 4;
     return m;
 }
+// TRI: the tri layout (c2 and its weak-scaled versions) with the loops over the four blocks of a group and their four logical
+// words unrolled and every offset a compile-time expression: the generic path spends 69 warp instructions per 32-sample word
+// (tables of offsets, tail / marginal / list bookkeeping on every lane), which made the packer issue-bound.
+template <bool TRI>
 static __global__ void __launch_bounds__(256) pack_rows_kernel(const uint8_t *__restrict__ raw, int64_t nv, int64_t nsamples,
                                                         const int32_t *__restrict__ perm, const FoldLayout *__restrict__ flp,
                                                         int64_t snp_pad, int64_t npos, uint32_t *__restrict__ planes) {
@@ -113,7 +117,7 @@ static __global__ void __launch_bounds__(256) pack_rows_kernel(const uint8_t *__
     for (int64_t x = tid; x < npos; x += blockDim.x) perm_s[x] = perm[x];
     // x: where logical word wb of plane 0 goes inside the staged output of one SNP; tri tails: -(offset + 1) | shift << 24
     // y: the marginal quad of its block | byte shift of the block's counter << 24 | 1 << 30 when the word is a tri tail
-    for (int wb = tid; wb < nwords; wb += blockDim.x) {
+    for (int wb = tid; wb < (TRI ? 0 : nwords); wb += blockDim.x) {
         const int b = wb >> lbw, w = wb & (bw - 1);
         int o;
         if (tri) o = w < 3 ? tri_word_off(b, 0, w) : -((tri_tail_off(nblocks, b, 0) + 1) | (tri_tail_shift(b) << 24));
@@ -145,6 +149,44 @@ static __global__ void __launch_bounds__(256) pack_rows_kernel(const uint8_t *__
             const int r = task / tasks_per_row, tg = task - r * tasks_per_row;
             uint32_t *dst = out_s + r * out_words;
             const uint8_t *row = row_s + mis + (size_t) r * nsamples;
+            if constexpr (TRI) {
+                // group tg = blocks 4 tg .. 4 tg + 3; logical word (q, w) sits at bit positions ((4 tg + q) * 4 + w) * 32 ..
+                const int32_t *pp = perm_s + (size_t) tg * 512 + lane;
+                uint32_t *grp = dst + tg * 36;
+                uint32_t nacc = 0, missacc = 0, tailacc = 0;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    uint32_t n = 0;
+                    bool miss_here = false;
+#pragma unroll
+                    for (int w = 0; w < 4; w++) {
+                        const int32_t col = pp[(q * 4 + w) * 32];
+                        const uint32_t g = col >= 0 ? row[col] : 255u;
+                        const uint32_t m0 = __ballot_sync(0xffffffffu, g == 0);
+                        const uint32_t m1 = __ballot_sync(0xffffffffu, g == 1);
+                        const uint32_t m2 = __ballot_sync(0xffffffffu, g == 2);
+                        miss_here |= (col >= 0 && g > 2u);
+                        uint32_t mine = lane == 0 ? m0 : (lane == 1 ? m1 : m2);
+                        if (w < 3) {
+                            if (lane < 3) grp[lane * 12 + q * 3 + w] = mine;
+                        } else {                                                   // the block's 4-bit tail
+                            mine &= 0xFu;
+                            tailacc |= mine << (group_shift(q) + 4 * (tg & 1));    // = tri_tail_shift(4 tg + q)
+                        }
+                        n += (uint32_t) __popc(mine);
+                    }
+                    nacc += n << group_shift(q);
+                    if (__any_sync(0xffffffffu, miss_here)) missacc |= 0xFFu << group_shift(q);
+                }
+                const int mq = marg_off + tg * 4;
+                if (lane < 3) {
+                    if (tailacc) atomicOr(dst + (nblocks >> 2) * 36 + (tg >> 1) * 4 + lane, tailacc);   // shared with the neighbouring group
+                    dst[mq + lane] = nacc;
+                } else if (lane == 3) {
+                    dst[mq + 3] = missacc;
+                }
+                continue;
+            }
             uint32_t nacc = 0, missacc = 0, tailacc = 0, my_ent = 0;     // my_ent: lane e keeps entry e of the group's missing list
             int tail_o = 0, mq = 0, nent = 0;
             for (int q = 0; q < bpt; q++) {
