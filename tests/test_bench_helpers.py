@@ -2,6 +2,7 @@
 window and throttle-reason parsing, and the reference arm's argument handling."""
 import argparse
 import math
+import numpy as np
 import os
 import sys
 
@@ -64,3 +65,42 @@ def test_reference_arm_runs_on_rank_zero_only(monkeypatch, capsys):
     monkeypatch.setenv("RANK", "3")
     bench.run_reference_arm(_args(impl="reference", gpus=8))                  # other ranks: no work, no output
     assert capsys.readouterr().out == ""
+
+
+class _OracleAsEngine:
+    """bench.parity_check takes the GPU engine for its 10^6-tuple sample; on the CPU the oracle answers in its place."""
+
+    def __init__(self, oracle, g, A, U, fos):
+        self.o, self.g, self.A, self.U, self.fos = oracle, g, A, U, fos
+
+    def eval(self, order, combs, subset):
+        return self.o.eval(self.g, self.A, self.U, order, self.fos, subset, combs)
+
+
+def test_parity_check_accepts_a_correct_result_and_flags_a_wrong_one(oracle):
+    """bench.py's parity_check (oracle re-score + sample check of the models a bench run returns) must pass on the true
+    ranking and fail when a model is altered, dropped from the top, or listed out of order."""
+    import bench
+    from hpg_variant_b200 import synth
+    from hpg_variant_b200._lib import MODEL_DTYPE
+    nv, A, U, F, rank = 60, 80, 80, 3, 8
+    g = synth.make_dataset(nv, A, U, seed=5, missing=0.01, planted=2)
+    fos = (np.concatenate([np.arange(A), np.arange(U)]) % F).astype(np.int32)
+    want, _ = oracle.search(g, A, U, 2, fos, 1, rank, threads=2, num_folds=F)
+    good = np.zeros((F, rank), MODEL_DTYPE)
+    good["accuracy"], good["snp"], good["risky_mask"], good["conf"] = want["ba"], want["snp"], want["risky_mask"], want["conf"]
+    w = dict(nv=nv, A=A, U=U, order=2, folds=F)
+    eng = _OracleAsEngine(oracle, g, A, U, fos)
+    res = bench.parity_check(eng, w, g, fos, good, 0, nv * (nv - 1) // 2, budget_s=20.0, gpu_samples=3000)
+    assert res["ok"] and res["violations"] == 0 and res["models_rescored"] == F * rank and res["gpu_samples"] >= 2000
+    bad = good.copy()
+    bad["conf"][1, 2, 0] += 1                                   # a confusion matrix that does not re-score
+    assert not bench.parity_check(eng, w, g, fos, bad, 0, 1, budget_s=5.0, gpu_samples=200)["ok"]
+    bad = good.copy()
+    bad[0, :-1] = good[0, 1:]                                   # the best model of fold 0 is missing from its list
+    bad[0, -1] = good[0, -1]
+    bad[0, -2] = good[0, -1]
+    assert not bench.parity_check(eng, w, g, fos, bad, 0, 1, budget_s=20.0, gpu_samples=4000)["ok"]
+    bad = good.copy()
+    bad[2, [0, 1]] = good[2, [1, 0]]                            # out of order
+    assert not bench.parity_check(eng, w, g, fos, bad, 0, 1, budget_s=5.0, gpu_samples=200)["ok"]

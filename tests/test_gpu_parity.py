@@ -339,3 +339,47 @@ def test_packer_roundtrip(engine, oracle, nv, A, U, F):
             want[:A] = np.where(g[v, :A] == gt, 255, 0)
             want[a_pad:a_pad + U] = np.where(g[v, A:] == gt, 255, 0)
             assert np.array_equal(m[gt], want)
+
+
+@pytest.mark.parametrize("order", [2, 3])
+def test_edge_cases_empty_range_tiny_cohorts_and_errors(engine, oracle, order):
+    """Empty and one-combination ranges, the smallest cohorts the API accepts (folds without cases or controls: 0/0 = NaN like
+    the reference, NaN ranks last), a caller-owned device buffer that ends right after the matrix, and the argument errors."""
+    import torch
+    # (1) empty range and a range of one combination
+    nv, A, U, F, rank = 12, 40, 44, 4, 6
+    g = synth.make_dataset(nv, A, U, seed=order, order=order, missing=0.02, planted=1)
+    fos = random_folds(np.random.default_rng(3), A, U, F)
+    engine.load_dataset(g, A, U)
+    engine.set_folds(F, fos)
+    total = h.num_combinations(nv, order)
+    empty = engine.search(order, h.SUBSET_TRAINING, rank, 5, 5)
+    assert (empty["snp"] == -1).all() and np.isnan(empty["accuracy"]).all() and (empty["conf"] == 0).all()
+    one = engine.search(order, h.SUBSET_TRAINING, rank, total - 1, total)
+    want, _ = oracle.search(g, A, U, order, fos, 1, rank, first=total - 1, last=total, threads=1, num_folds=F)
+    compare_models(one, want, order)
+    assert (one["snp"][:, 0, :order] == np.arange(nv - order, nv)).all() and (one["snp"][:, 1:, 0] == -1).all()
+    # (2) tiny cohorts: 3 cases, 2 controls, 3 folds -> fold 2 holds a case and no control (testing part: TN + FP = 0 -> NaN)
+    nv, A, U, F = 5, 3, 2, 3
+    g = np.array([[0, 1, 2, 0, 1], [1, 1, 0, 2, 255], [2, 0, 0, 1, 1], [0, 0, 1, 1, 2], [255, 2, 1, 0, 0]], np.uint8)
+    fos = np.array([0, 1, 2, 0, 1], np.int32)
+    # the bytes live in a device buffer that ends with the matrix (pack_rows_kernel must not read 16-byte groups past it)
+    d = torch.from_numpy(g.reshape(-1).copy()).cuda()
+    engine.load_dataset_device(d.data_ptr(), nv, A, U)
+    engine.set_folds(F, fos)
+    for subset in (h.SUBSET_TRAINING, h.SUBSET_TESTING):
+        got = engine.search(order, subset, 4)
+        want, _ = oracle.search(g, A, U, order, fos, subset, 4, threads=1, num_folds=F)
+        compare_models(got, want, order)
+    combs = np.array(list(__import__("itertools").combinations(range(nv), order)), np.int32)
+    ev, ov = engine.eval(order, combs, h.SUBSET_TESTING), oracle.eval(g, A, U, order, fos, 0, combs)
+    assert np.array_equal(ev["conf"], ov["conf"]) and np.array_equal(ev["ba"], ov["ba"], equal_nan=True) and np.isnan(ev["ba"][:, 2]).all()
+    # (3) argument errors come back as codes, never as a crash or a CPU path
+    for bad in (lambda: engine.search(4, h.SUBSET_TRAINING, 4), lambda: engine.search(order, 7, 4), lambda: engine.search(order, h.SUBSET_TRAINING, 0),
+                lambda: engine.search(order, h.SUBSET_TRAINING, 5000), lambda: engine.eval(order, np.array([[3, 1, 0][:order]], np.int32)),
+                lambda: engine.set_folds(1, np.zeros(A + U, np.int32)), lambda: engine.set_folds(F, np.full(A + U, F, np.int32)),
+                lambda: engine.set_eval_function(h.EVAL_WBA), lambda: engine.set_eval_function(9)):
+        with pytest.raises(h.HpgvError):
+            bad()
+    engine.set_folds(F, fos)                              # the context is still usable afterwards
+    assert engine.search(order, h.SUBSET_TRAINING, 4).shape == (F, 4)
