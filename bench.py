@@ -99,7 +99,7 @@ class ClockSampler:
         if not shutil.which("nvidia-smi"):
             return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -437,6 +437,15 @@ class Runner:
             tmax, tmin = self.reduce(p, "MAX"), self.reduce(p, "MIN")
             names = ["pack+search", "all_gather(incl. wait for the slowest rank)", "merge", "search_kernel"]
             phases = {n: {"min_over_ranks": float(a), "max_over_ranks": float(b)} for n, a, b in zip(names, tmin, tmax)}
+        dump = os.environ.get("HPGV_BENCH_DUMP_STEPS")          # development: per-step times of every rank, one file per rank
+        if dump:
+            os.makedirs(dump, exist_ok=True)
+            rec = {"rank": rank, "step_ms": [a.elapsed_time(b) for a, b in ev], "search_kernel_ms": [float(x) for x in search_ms]}
+            if world > 1 and phase_ev:
+                rec["pack_search_ms"] = [ev[k][0].elapsed_time(phase_ev[k][0]) for k in range(steps)]
+                rec["gather_ms"] = [phase_ev[k][0].elapsed_time(phase_ev[k][1]) for k in range(steps)]
+            with open(os.path.join(dump, f"steps_{w['name'].split(':')[0]}_n{world}_rank{rank}.json"), "w") as fh:
+                json.dump(rec, fh)
         out = dict(w=w, g=g, fos=fos, total=total, first=first, last=last, dev_ms=dev_ms, steps=steps, search_ms=search_ms, k_ms=k_ms,
                    k_ms_min=kmin, k_ms_max=kmax, my_step_ms=my_dev_ms / steps, phases=phases, launches=launches, clocks=clocks,
                    t_wall=t_wall, first_call_s=first_call_s, value=total * F * steps / (dev_ms * 1e-3), lay=eng.layout(),
@@ -537,7 +546,7 @@ def main():
     eng = runner.eng
     w = workload(args, world)
     sampler = ClockSampler(runner.local_rank)
-    if rank == 0:                                   # rank 0's GPU is the one whose clocks the line reports
+    if rank == 0 and os.environ.get("HPGV_BENCH_NO_SAMPLER") != "1":    # rank 0's GPU is the one whose clocks the line reports
         sampler.start()
     r = runner.run(w, args.steps, args.warmup, sampler=sampler, e2e=True)
     w = r["w"]

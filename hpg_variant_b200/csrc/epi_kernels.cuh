@@ -2354,8 +2354,12 @@ __device__ __forceinline__ bool key_prefix_eq(const Key128 &k, const Key128 &p, 
 }
 
 constexpr int kMergeThreads = 1024;
-constexpr int kMergeSmall = 2048;        // up to this many valid entries per fold are ranked by counting in shared memory
-__host__ __device__ inline size_t merge_smem_bytes(int rank_out) { return (size_t) rank_out * 20 + 16 + (size_t) kMergeSmall * 20; }
+constexpr int kMergeSort = 8192;         // up to this many valid entries per fold are sorted in shared memory (148 lists x 50 = 7400)
+// the sorted (key, slot) arrays and the selection arrays of the general path share the same bytes: a fold takes one path or the other
+__host__ __device__ inline size_t merge_smem_bytes(int rank_out) {
+    const size_t sel = (size_t) rank_out * 20 + 16, srt = (size_t) kMergeSort * 20;
+    return sel > srt ? sel : srt;
+}
 
 static __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeArgs m) {
     extern __shared__ __align__(16) uint8_t msmem[];
@@ -2381,46 +2385,62 @@ static __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const Merge
     };
 
     // valid entries are counted and, while they fit, compacted (key, slot) into shared memory
-    Key128 *ckey = reinterpret_cast<Key128 *>(msmem + (((size_t) m.rank_out * 20 + 15) / 16) * 16);   // [kMergeSmall]
-    int *cidx = reinterpret_cast<int *>(ckey + kMergeSmall);                                            // [kMergeSmall]
+    Key128 *ckey = reinterpret_cast<Key128 *>(msmem);           // [kMergeSort]
+    int *cidx = reinterpret_cast<int *>(ckey + kMergeSort);     // [kMergeSort]
     if (tid == 0) { prefix.hi = 0; prefix.lo = 0; nsel = 0; nvalid_sh = 0; }
     __syncthreads();
     for (int e = tid; e < total; e += kMergeThreads) {
         Cand c;
         if (!entry_valid(e, c)) continue;
         const int pos = atomicAdd(&nvalid_sh, 1);
-        if (pos < kMergeSmall) { ckey[pos] = cand_key(c, m.order); cidx[pos] = e; }
+        if (pos < kMergeSort) { ckey[pos] = cand_key(c, m.order); cidx[pos] = e; }
     }
     __syncthreads();
-    if (nvalid_sh <= kMergeSmall) {
-        // Few entries (the usual case when the score histogram keeps the lists short): keys are unique, so the rank of an
-        // entry is the number of larger keys -- counted against the compacted keys, no selection passes.
+    if (nvalid_sh <= kMergeSort) {
+        // The usual case (148 per-CTA lists of 50, or the lists of 8 ranks): a bitonic sort of the compacted keys, descending.
+        // Its cost depends on the number of entries only through the power of two above it -- a rank whose lists are full
+        // takes as long as one whose lists the score histogram kept short (the counting / radix-select it replaces took
+        // 90 us and 255 us for the two halves of a 2-GPU pair range; every other rank waits for the slowest in the all-gather).
         const int n = nvalid_sh;
-        ModelOut *out = reinterpret_cast<ModelOut *>(m.out) + (size_t) f * m.rank_out;
-        for (int t = tid; t < n; t += kMergeThreads) {
-            const Key128 k = ckey[t];
-            int rank = 0;
-            for (int o = 0; o < n; o++) rank += key_gt(ckey[o], k) ? 1 : 0;
-            if (rank >= m.rank_out) continue;
-            const Cand c = *entry(cidx[t]);
-            ModelOut r;
-            r.accuracy = (degenerate || c.ba == -INFINITY) ? nan("") : c.ba;
-            r.snp[0] = c.i; r.snp[1] = c.j; r.snp[2] = m.order == 3 ? c.k : -1;
-            r.risky_mask = c.mask;
-            r.conf[0] = (uint32_t) c.tp; r.conf[1] = (uint32_t) (npos - c.tp);
-            r.conf[2] = (uint32_t) c.fp; r.conf[3] = (uint32_t) (nneg - c.fp);
-            out[rank] = r;
+        int P = 32;
+        while (P < n) P <<= 1;
+        for (int t = n + tid; t < P; t += kMergeThreads) { ckey[t].hi = 0; ckey[t].lo = 0; cidx[t] = -1; }   // below every real key
+        __syncthreads();
+        for (int k = 2; k <= P; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < P / 2; t += kMergeThreads) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                    const Key128 a = ckey[i], b = ckey[l];
+                    const bool desc = (i & k) == 0;
+                    if (desc ? key_gt(b, a) : key_gt(a, b)) {
+                        ckey[i] = b; ckey[l] = a;
+                        const int x = cidx[i]; cidx[i] = cidx[l]; cidx[l] = x;
+                    }
+                }
+                __syncthreads();
+            }
         }
-        for (int t = min(n, m.rank_out) + tid; t < m.rank_out; t += kMergeThreads) {
+        ModelOut *out = reinterpret_cast<ModelOut *>(m.out) + (size_t) f * m.rank_out;
+        for (int t = tid; t < m.rank_out; t += kMergeThreads) {
             ModelOut r;
-            r.accuracy = nan("");
-            r.snp[0] = r.snp[1] = r.snp[2] = -1;
-            r.risky_mask = 0;
-            r.conf[0] = r.conf[1] = r.conf[2] = r.conf[3] = 0;
+            if (t < n) {
+                const Cand c = *entry(cidx[t]);
+                r.accuracy = (degenerate || c.ba == -INFINITY) ? nan("") : c.ba;
+                r.snp[0] = c.i; r.snp[1] = c.j; r.snp[2] = m.order == 3 ? c.k : -1;
+                r.risky_mask = c.mask;
+                r.conf[0] = (uint32_t) c.tp; r.conf[1] = (uint32_t) (npos - c.tp);
+                r.conf[2] = (uint32_t) c.fp; r.conf[3] = (uint32_t) (nneg - c.fp);
+            } else {
+                r.accuracy = nan("");
+                r.snp[0] = r.snp[1] = r.snp[2] = -1;
+                r.risky_mask = 0;
+                r.conf[0] = r.conf[1] = r.conf[2] = r.conf[3] = 0;
+            }
             out[t] = r;
         }
         return;
     }
+    __syncthreads();                     // the selection arrays below reuse the bytes of the compacted keys
     const int want = min(m.rank_out, nvalid_sh);
     if (tid == 0) want_sh = want;
     __syncthreads();
