@@ -83,7 +83,8 @@ int main() {
         CHECK(p.ofs == 20 * 128 * 4 && p.row % 16 == 0 && p.out % 16 == 0 && p.total == p.out + (size_t) kPackRows * fl.row_words * 4, "pack map");
         CHECK(hist_coarse_bins(1001) == 32 && hist_coarse_bins(32) == 1 && hist_coarse_bins(33) == 2, "hist_coarse_bins");
         CHECK(counter_stride(9, 5) % 2 == 1 && counter_stride(27, 5) % 2 == 1, "counter stride must be odd");
-        CHECK(merge_smem_bytes(50) >= (size_t) 50 * 20 + (size_t) kMergeSmall * 20, "merge smem");
+        CHECK(merge_smem_bytes(50) >= (size_t) kMergeSort * 20 && merge_smem_bytes(4096) >= (size_t) 4096 * 20 + 16 && merge_smem_bytes(4096) <= 227 * 1024
+              && kMergeSort >= 148 * 50 && (kMergeSort & (kMergeSort - 1)) == 0, "merge smem");
     }
     printf(fails ? "%d check(s) failed\n" : "layout checks ok\n", fails);
     return fails ? 1 : 0;
