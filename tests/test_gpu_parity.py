@@ -383,3 +383,28 @@ def test_edge_cases_empty_range_tiny_cohorts_and_errors(engine, oracle, order):
             bad()
     engine.set_folds(F, fos)                              # the context is still usable afterwards
     assert engine.search(order, h.SUBSET_TRAINING, 4).shape == (F, 4)
+
+
+@pytest.mark.parametrize("order,nv,A,U,F,rank", [(2, 420, 300, 200, 3, 300), (2, 150, 500, 500, 5, 3000), (3, 60, 240, 200, 3, 300)])
+def test_merge_long_lists_take_the_selection_path(engine, oracle, order, nv, A, U, F, rank):
+    """More than 8192 valid list entries per fold (long rankings, every CTA's list full): merge_kernel leaves the
+    shared-memory sort for the radix select over global memory.  Whole search against the oracle, and four sub-range
+    rankings merged on the device (the multi-GPU merge at a long rank size) against the whole search."""
+    import torch
+    g = synth.make_dataset(nv, A, U, seed=nv + rank, order=order, missing=0.01, planted=2)
+    fos = random_folds(np.random.default_rng(rank), A, U, F)
+    engine.load_dataset(g, A, U)
+    engine.set_folds(F, fos)
+    total = h.num_combinations(nv, order)
+    assert min(total, 148 * rank) > 8192
+    full = engine.search(order, h.SUBSET_TRAINING, rank)
+    want, _ = oracle.search(g, A, U, order, fos, h.SUBSET_TRAINING, rank, threads=8, num_folds=F)
+    compare_models(full, want, order)
+    cuts = [0, total // 5, total // 2, total - total // 7, total]
+    parts = [engine.search(order, h.SUBSET_TRAINING, rank, cuts[i], cuts[i + 1]) for i in range(4)]
+    lists = torch.from_numpy(np.stack(parts).view(np.uint8)).cuda()
+    out = torch.zeros(F * rank * 40, dtype=torch.uint8, device="cuda")
+    engine.merge_device(order, h.SUBSET_TRAINING, 4, rank, lists.data_ptr(), out.data_ptr())
+    torch.cuda.synchronize()
+    merged = out.cpu().numpy().view(h.MODEL_DTYPE).reshape(F, rank)
+    assert merged.tobytes() == full.tobytes()
